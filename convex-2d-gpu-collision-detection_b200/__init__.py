@@ -1,0 +1,247 @@
+"""satmc-b200: B200-native Monte Carlo SAT collision probability (Python host mirror).
+
+Thin ctypes binding over the C ABI in ``include/satmc.h`` (``libsatmc.so``, hand-written CUDA for
+sm_100a).  The reference (beautifulv0id/Convex-2D-GPU-Collision-Detection) has no Python API; its
+host side is three CUDA C++ programs, so the real host layer lives in ``host/`` (C++).  This module
+exists for the tests, ``bench.py`` and multi-GPU plumbing (``torch.distributed``): PyTorch supplies
+device memory and streams, nothing else.
+
+There is NO CPU fallback: importing works anywhere (so the C-ABI symbol test can run without a
+GPU) but creating a :class:`Context` raises unless a sm_100 device is present, and a missing
+``libsatmc.so`` raises at import of the library handle.
+
+The package directory name contains hyphens; import it with
+``importlib.import_module("convex-2d-gpu-collision-detection_b200")`` (see ``tests/conftest.py``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsatmc.so")
+INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
+
+SATMC_ACCUMULATE = 0x1
+SATMC_EXACT_ONLY = 0x2
+
+#: numpy dtype of ``satmc_pair`` (include/satmc.h) -- 12 packed float32 = 48 bytes
+PAIR_DTYPE = np.dtype([(n, "<f4") for n in
+                       ("rx", "ry", "rtheta", "rw", "rh", "ow", "oh", "sd_x", "sd_y", "sd_theta", "sd_w", "sd_h")])
+PAIR_FIELDS = PAIR_DTYPE.names
+
+#: every symbol include/satmc.h declares (checked against the built library by tests/test_abi.py)
+ABI_SYMBOLS = (
+    "satmc_create", "satmc_destroy", "satmc_synchronize", "satmc_last_error", "satmc_version",
+    "satmc_launch_count", "satmc_set_profiling", "satmc_last_kernel_ms",
+    "satmc_count_fused", "satmc_count_streamed", "satmc_decide_streamed", "satmc_fused_normals",
+    "satmc_philox_blocks", "satmc_sat_corners", "satmc_exact_evals",
+    "satmc_mc_step", "satmc_write_collision_probability",
+    "satmc_count_fused_host", "satmc_count_streamed_host", "satmc_collision_probability_host",
+    "satmc_host_alloc", "satmc_host_free",
+)
+
+
+class SatmcError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"satmc error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Loads ``libsatmc.so`` (built in-tree by ``__graft_entry__.build()`` / ``make``). Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp, u64, u32, i32, f32p = c.c_void_p, c.c_uint64, c.c_uint32, c.c_int, c.c_void_p
+    sig = {
+        "satmc_create": (i32, [i32, vp, c.POINTER(vp)]),
+        "satmc_destroy": (i32, [vp]),
+        "satmc_synchronize": (i32, [vp]),
+        "satmc_last_error": (c.c_char_p, [vp]),
+        "satmc_version": (c.c_char_p, []),
+        "satmc_launch_count": (u64, [vp]),
+        "satmc_set_profiling": (i32, [vp, i32]),
+        "satmc_last_kernel_ms": (c.c_float, [vp]),
+        "satmc_count_fused": (i32, [vp, vp, u64, u64, u64, u64, u32, vp, u32]),
+        "satmc_count_streamed": (i32, [vp, vp, u64, f32p, u64, u64, i32, u64, vp, u32]),
+        "satmc_decide_streamed": (i32, [vp, vp, f32p, u64, i32, u64, vp, u32]),
+        "satmc_fused_normals": (i32, [vp, u64, u32, u64, u64, f32p, u64]),
+        "satmc_philox_blocks": (i32, [vp, vp, u64, u32, u32, vp]),
+        "satmc_sat_corners": (i32, [vp, f32p, f32p, u64, vp]),
+        "satmc_exact_evals": (i32, [vp, c.POINTER(u64), i32]),
+        "satmc_mc_step": (i32, [vp, f32p, f32p, u32, f32p, u32, f32p, f32p, f32p, f32p, f32p, f32p, i32, vp,
+                                i32, i32, i32, i32, u64, u32]),
+        "satmc_write_collision_probability": (i32, [vp, f32p, i32, i32]),
+        "satmc_count_fused_host": (i32, [vp, vp, u64, u64, u64, u64, u32, vp, u32]),
+        "satmc_count_streamed_host": (i32, [vp, vp, u64, f32p, u64, u64, i32, u64, vp, u32]),
+        "satmc_collision_probability_host": (i32, [vp, vp, u64, u64, u64, f32p]),
+        "satmc_host_alloc": (i32, [c.POINTER(vp), c.c_size_t]),
+        "satmc_host_free": (i32, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def make_pairs(n: int) -> np.ndarray:
+    """Zero-initialised structured array of ``n`` pairs."""
+    return np.zeros(n, dtype=PAIR_DTYPE)
+
+
+def pairs_from_columns(rx, ry, rtheta, ow, oh, sd_x, sd_y, sd_theta, sd_w=0.0, sd_h=0.0,
+                       rw=4.07, rh=1.74) -> np.ndarray:
+    """Builds the pair array from broadcastable columns (robot defaults: generate_dataset.cu:60-61)."""
+    cols = np.broadcast_arrays(*[np.asarray(a, dtype=np.float32) for a in
+                                 (rx, ry, rtheta, rw, rh, ow, oh, sd_x, sd_y, sd_theta, sd_w, sd_h)])
+    out = make_pairs(cols[0].size)
+    for name, col in zip(PAIR_FIELDS, cols):
+        out[name] = col.ravel()
+    return out
+
+
+def _ptr(x) -> int:
+    """Raw address of a torch CUDA tensor, numpy array, or int."""
+    if x is None:
+        return 0
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return x.data_ptr()          # torch.Tensor
+
+
+class Context:
+    """One satmc context = one GPU + one stream (``satmc_create``)."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self._lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self._lib.satmc_create(int(device), ctypes.c_void_p(stream or 0), ctypes.byref(h))
+        if rc != 0:
+            raise SatmcError(rc, self._lib.satmc_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+
+    # -- plumbing -----------------------------------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise SatmcError(rc, self._lib.satmc_last_error(self._h).decode())
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.satmc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def synchronize(self) -> None:
+        self._check(self._lib.satmc_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.satmc_launch_count(self._h))
+
+    def set_profiling(self, on: bool) -> None:
+        self._check(self._lib.satmc_set_profiling(self._h, int(bool(on))))
+
+    def last_kernel_ms(self) -> float:
+        return float(self._lib.satmc_last_kernel_ms(self._h))
+
+    def exact_evals(self, reset: bool = False) -> int:
+        v = ctypes.c_uint64()
+        self._check(self._lib.satmc_exact_evals(self._h, ctypes.byref(v), int(reset)))
+        return int(v.value)
+
+    # -- device-pointer entry points (torch CUDA tensors or raw addresses) -----------------------
+    def count_fused(self, d_pairs, n_pairs, n_samples, seed, d_hits, sample_offset=0, pair_id_offset=0, flags=0):
+        self._check(self._lib.satmc_count_fused(self._h, _ptr(d_pairs), n_pairs, n_samples, seed, sample_offset,
+                                                pair_id_offset, _ptr(d_hits), flags))
+
+    def count_streamed(self, d_pairs, n_pairs, d_z, ldz, ndof, n_samples, d_hits, z_pair_stride=0, flags=0):
+        self._check(self._lib.satmc_count_streamed(self._h, _ptr(d_pairs), n_pairs, _ptr(d_z), ldz, z_pair_stride,
+                                                   ndof, n_samples, _ptr(d_hits), flags))
+
+    def decide_streamed(self, d_pair, d_z, ldz, ndof, n_samples, d_out, flags=0):
+        self._check(self._lib.satmc_decide_streamed(self._h, _ptr(d_pair), _ptr(d_z), ldz, ndof, n_samples,
+                                                    _ptr(d_out), flags))
+
+    def fused_normals(self, seed, pair_id, sample_offset, n, d_z, ldz):
+        self._check(self._lib.satmc_fused_normals(self._h, seed, pair_id, sample_offset, n, _ptr(d_z), ldz))
+
+    def philox_blocks(self, d_ctr, n, key0, key1, d_out):
+        self._check(self._lib.satmc_philox_blocks(self._h, _ptr(d_ctr), n, key0, key1, _ptr(d_out)))
+
+    def sat_corners(self, d_r1, d_r2, n, d_out):
+        self._check(self._lib.satmc_sat_corners(self._h, _ptr(d_r1), _ptr(d_r2), n, _ptr(d_out)))
+
+    def mc_step(self, d_robot_base, d_poses, n_poses, d_std_devs, n_std, d_pose_idxs, d_std_dev_idxs, d_positions,
+                d_cps, d_accuracy_bins, d_bin_accuracy, n_accuracy_bins, d_done, iteration, n_samples, n_batch,
+                num_left, seed, stream_id_offset=0):
+        self._check(self._lib.satmc_mc_step(self._h, _ptr(d_robot_base), _ptr(d_poses), n_poses, _ptr(d_std_devs),
+                                            n_std, _ptr(d_pose_idxs), _ptr(d_std_dev_idxs), _ptr(d_positions),
+                                            _ptr(d_cps), _ptr(d_accuracy_bins), _ptr(d_bin_accuracy),
+                                            n_accuracy_bins, _ptr(d_done), iteration, n_samples, n_batch, num_left,
+                                            seed, stream_id_offset))
+
+    def write_collision_probability(self, d_counts, n_done, n_samples):
+        self._check(self._lib.satmc_write_collision_probability(self._h, _ptr(d_counts), n_done, n_samples))
+
+    # -- host-buffer entry points (numpy) -----------------------------------------------------------
+    def count_fused_host(self, pairs: np.ndarray, n_samples: int, seed: int, sample_offset: int = 0,
+                         pair_id_offset: int = 0, flags: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
+        hits = out if out is not None else np.zeros(pairs.size, dtype=np.uint64)
+        self._check(self._lib.satmc_count_fused_host(self._h, pairs.ctypes.data, pairs.size, n_samples, seed,
+                                                     sample_offset, pair_id_offset, hits.ctypes.data, flags))
+        return hits
+
+    def count_streamed_host(self, pairs: np.ndarray, z: np.ndarray, n_samples: Optional[int] = None,
+                            z_pair_stride: int = 0, flags: int = 0) -> np.ndarray:
+        """``z`` is ``[ndof, ldz]`` float32 (SoA planes)."""
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
+        z = np.ascontiguousarray(z, dtype=np.float32)
+        ndof, ldz = z.shape
+        if n_samples is None:
+            n_samples = ldz if z_pair_stride == 0 else z_pair_stride
+        hits = np.zeros(pairs.size, dtype=np.uint64)
+        self._check(self._lib.satmc_count_streamed_host(self._h, pairs.ctypes.data, pairs.size, z.ctypes.data, ldz,
+                                                        z_pair_stride, ndof, n_samples, hits.ctypes.data, flags))
+        return hits
+
+    def collision_probability_host(self, pairs: np.ndarray, n_samples: int, seed: int) -> np.ndarray:
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
+        cp = np.zeros(pairs.size, dtype=np.float32)
+        self._check(self._lib.satmc_collision_probability_host(self._h, pairs.ctypes.data, pairs.size, n_samples, seed,
+                                                               cp.ctypes.data))
+        return cp
+
+
+def compute_collision_probability(pairs: np.ndarray, n_samples: int, seed: int = 0, device: int = 0) -> np.ndarray:
+    """One-shot convenience: collision probability of every pair from ``n_samples`` fused samples."""
+    with Context(device) as ctx:
+        return ctx.collision_probability_host(pairs, n_samples, seed)

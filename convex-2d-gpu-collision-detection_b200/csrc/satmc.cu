@@ -1,0 +1,759 @@
+// satmc.cu -- kernels and C ABI of the B200-native Monte Carlo SAT path (sm_100a).
+//
+// Work decomposition: a work item is (pair, sample chunk); one warp owns one
+// item at a time (grid-stride over items), its 32 lanes stride over the samples of the chunk, each
+// lane keeps a private hit counter, and the item ends with one REDUX warp reduction and one store
+// or one atomic.  When every warp of a block works on the same pair the warp sums are combined in
+// shared memory first and the block issues a single 64-bit atomic.
+//
+// The reference does the opposite (one thread = one pair, serial over samples, RNG state in global
+// memory, ztest.cu:122-155), which starves the GPU whenever pairs < resident threads.
+#include "../../include/satmc.h"
+
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "satmc_geom.cuh"
+#include "satmc_sampler.cuh"
+
+namespace satmc {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+// ---------------------------------------------------------------------------------------------
+// pair sources
+// ---------------------------------------------------------------------------------------------
+struct DirectSrc {
+    const satmc_pair* pairs;
+    __device__ __forceinline__ void load(uint64_t i, float v[12]) const {
+        const float4* p = reinterpret_cast<const float4*>(pairs + i);   // 48 B, 16-B aligned
+        const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y;
+        v[6] = b.z; v[7] = b.w; v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+    }
+};
+
+// The reference's indirect layout (ztest.cu:135-140): per live pair a position and two float indices
+// into the pose and std-dev tables; the robot is create_rect(robot_w, robot_h).
+struct IndirectSrc {
+    const float* robot_base; const float* poses; const float* std_devs;
+    const float* pose_idxs; const float* std_dev_idxs; const float* positions;
+    uint32_t n_poses, n_std;
+    __device__ __forceinline__ void load(uint64_t i, float v[12]) const {
+        uint32_t pi = (uint32_t)(int)__ldg(pose_idxs + i);
+        uint32_t si = (uint32_t)(int)__ldg(std_dev_idxs + i);
+        pi = pi < n_poses ? pi : n_poses - 1;          // the reference would read out of bounds
+        si = si < n_std ? si : n_std - 1;
+        v[0] = __ldg(positions + 2 * i); v[1] = __ldg(positions + 2 * i + 1);
+        v[2] = __ldg(poses + 3 * (size_t)pi + 2);
+        v[3] = 2.0f * __ldg(robot_base + 2);           // create_rect: r[2] = w/2, r[5] = h/2 (exact)
+        v[4] = 2.0f * __ldg(robot_base + 5);
+        v[5] = __ldg(poses + 3 * (size_t)pi); v[6] = __ldg(poses + 3 * (size_t)pi + 1);
+#pragma unroll
+        for (int k = 0; k < 5; k++) v[7 + k] = __ldg(std_devs + 5 * (size_t)si + k);
+    }
+};
+
+struct CountParams {
+    uint64_t n_pairs;
+    uint64_t n_samples;        // per pair
+    uint64_t sample_offset;    // fused: first sample index
+    uint64_t chunk;            // samples per work item (multiple of 128)
+    uint64_t n_items;          // n_pairs * n_chunks
+    uint32_t n_chunks;
+    uint32_t pair_id_offset;
+    uint32_t k0, k1;
+    uint32_t flags;            // SATMC_ACCUMULATE | SATMC_EXACT_ONLY
+    uint32_t block_uniform;    // all warps of a block share a pair -> block reduction
+    unsigned long long* hits;
+    unsigned long long* exact_evals;
+    // streamed
+    const float* z; uint64_t ldz; uint64_t z_pair_stride; int ndof; int vec_ok;
+};
+
+// one sample of the fused path
+template <int NDOF>
+__device__ __forceinline__ unsigned fused_sample(const PairConst& P, const float* robot, uint64_t s, uint32_t pid,
+                                                 uint32_t k0, uint32_t k1, unsigned long long* exact_evals)
+{
+    float z0, z1, z2, z3, z4 = 0.0f;
+    normals4<NDOF == 5>((uint32_t)s, (uint32_t)(s >> 32), pid, k0, k1, z0, z1, z2, z3);
+    if (NDOF == 5) z4 = normal5th((uint32_t)s, (uint32_t)(s >> 32), pid, k0, k1);
+    const float m = screen_gap<NDOF>(P, z0, z1, z2, z3, z4);
+    unsigned hit = m < 0.0f;
+    if (!(fabsf(m) > P.eps)) {                                      // undecided (or NaN): exact arithmetic
+        hit = (unsigned)exact_decide(robot, P.ow, P.oh, P.sd_x, P.sd_y, P.sd_t, P.sd_w, P.sd_h, z0, z1, z2, z3, z4);
+        if (exact_evals) atomicAdd(exact_evals, 1ull);
+    }
+    return hit;
+}
+
+// one sample of the streamed path (normals supplied)
+template <int NDOF>
+__device__ __forceinline__ unsigned streamed_sample(const PairConst& P, const float* robot, float z0, float z1,
+                                                    float z2, float z3, float z4, unsigned long long* exact_evals)
+{
+    const float m = screen_gap<NDOF>(P, z0, z1, z2, z3, z4);
+    unsigned hit = m < 0.0f;
+    // the screening bound assumes |z| <= SATMC_Z_BOUND; ">" is false for NaN, so NaN/Inf go exact
+    bool ok = fabsf(m) > P.eps;
+    ok = ok && (fabsf(z0) <= SATMC_Z_BOUND) && (fabsf(z1) <= SATMC_Z_BOUND) && (fabsf(z2) <= SATMC_Z_BOUND);
+    if (NDOF == 5) ok = ok && (fabsf(z3) <= SATMC_Z_BOUND) && (fabsf(z4) <= SATMC_Z_BOUND);
+    if (!ok) {
+        hit = (unsigned)exact_decide(robot, P.ow, P.oh, P.sd_x, P.sd_y, P.sd_t, P.sd_w, P.sd_h, z0, z1, z2, z3, z4);
+        if (exact_evals) atomicAdd(exact_evals, 1ull);
+    }
+    return hit;
+}
+
+template <int NDOF>
+__device__ __forceinline__ unsigned fused_chunk(const PairConst& P, const float* robot, uint64_t s_begin, uint64_t len,
+                                                uint32_t pid, uint32_t k0, uint32_t k1, int lane,
+                                                unsigned long long* exact_evals)
+{
+    unsigned cnt = 0;
+    uint64_t i = (uint64_t)lane;
+    // two independent samples per trip: hides the serial Philox round chain
+    for (; i + 32 < len; i += 64) {
+        cnt += fused_sample<NDOF>(P, robot, s_begin + i, pid, k0, k1, exact_evals);
+        cnt += fused_sample<NDOF>(P, robot, s_begin + i + 32, pid, k0, k1, exact_evals);
+    }
+    if (i < len) cnt += fused_sample<NDOF>(P, robot, s_begin + i, pid, k0, k1, exact_evals);
+    return cnt;
+}
+
+template <int NDOF>
+__device__ __forceinline__ unsigned streamed_chunk(const PairConst& P, const float* robot, const float* __restrict__ z,
+                                                   uint64_t ldz, uint64_t len, int vec_ok, int lane,
+                                                   unsigned long long* exact_evals)
+{
+    unsigned cnt = 0;
+    uint64_t done = 0;
+    if (vec_ok) {
+        const uint64_t nvec = len / 4;
+        for (uint64_t v = (uint64_t)lane; v < nvec; v += 32) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(z) + v);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(z + ldz) + v);
+            const float4 c = __ldg(reinterpret_cast<const float4*>(z + 2 * ldz) + v);
+            float4 d = make_float4(0.f, 0.f, 0.f, 0.f), e = d;
+            if (NDOF == 5) {
+                d = __ldg(reinterpret_cast<const float4*>(z + 3 * ldz) + v);
+                e = __ldg(reinterpret_cast<const float4*>(z + 4 * ldz) + v);
+            }
+            cnt += streamed_sample<NDOF>(P, robot, a.x, b.x, c.x, d.x, e.x, exact_evals);
+            cnt += streamed_sample<NDOF>(P, robot, a.y, b.y, c.y, d.y, e.y, exact_evals);
+            cnt += streamed_sample<NDOF>(P, robot, a.z, b.z, c.z, d.z, e.z, exact_evals);
+            cnt += streamed_sample<NDOF>(P, robot, a.w, b.w, c.w, d.w, e.w, exact_evals);
+        }
+        done = nvec * 4;
+    }
+    for (uint64_t i = done + (uint64_t)lane; i < len; i += 32) {
+        const float z0 = __ldg(z + i), z1 = __ldg(z + ldz + i), z2 = __ldg(z + 2 * ldz + i);
+        float z3 = 0.f, z4 = 0.f;
+        if (NDOF == 5) { z3 = __ldg(z + 3 * ldz + i); z4 = __ldg(z + 4 * ldz + i); }
+        cnt += streamed_sample<NDOF>(P, robot, z0, z1, z2, z3, z4, exact_evals);
+    }
+    return cnt;
+}
+
+template <class Src, bool STREAMED>
+__global__ void __launch_bounds__(kThreads) k_count(Src src, CountParams p)
+{
+    __shared__ float s_robot[kWarps][8];
+    __shared__ unsigned s_part[kWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t)gridDim.x * kWarps;
+    // items are laid out pair-major; with block_uniform all 8 warps of a block walk the loop in step
+    for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < p.n_items; item += stride) {
+        const uint64_t pair = item / p.n_chunks;
+        const uint32_t chunk_id = (uint32_t)(item - pair * p.n_chunks);
+        float v[12];
+        src.load(pair, v);
+        PairConst P;
+        pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
+        if (p.flags & SATMC_EXACT_ONLY) P.eps = CUDART_INF_F;
+        __syncwarp();
+        if (lane == 0) exact_robot_corners(v[0], v[1], v[2], v[3], v[4], s_robot[warp]);
+        __syncwarp();
+        const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
+        const uint64_t c_len = (c_begin + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - c_begin);
+        unsigned long long* ev = (p.flags & SATMC_EXACT_ONLY) ? nullptr : p.exact_evals;
+        unsigned cnt;
+        if (STREAMED) {
+            const float* z = p.z + pair * p.z_pair_stride + c_begin;
+            cnt = (p.ndof == 5) ? streamed_chunk<5>(P, s_robot[warp], z, p.ldz, c_len, p.vec_ok, lane, ev)
+                                : streamed_chunk<3>(P, s_robot[warp], z, p.ldz, c_len, p.vec_ok, lane, ev);
+        } else {
+            const uint32_t pid = p.pair_id_offset + (uint32_t)pair;
+            const uint64_t s_begin = p.sample_offset + c_begin;
+            const bool dof3 = (v[10] == 0.0f) && (v[11] == 0.0f);
+            cnt = dof3 ? fused_chunk<3>(P, s_robot[warp], s_begin, c_len, pid, p.k0, p.k1, lane, ev)
+                       : fused_chunk<5>(P, s_robot[warp], s_begin, c_len, pid, p.k0, p.k1, lane, ev);
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (p.block_uniform) {
+            if (lane == 0) s_part[warp] = cnt;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long t = 0;
+#pragma unroll
+                for (int w = 0; w < kWarps; w++) t += s_part[w];
+                atomicAdd(p.hits + pair, t);                       // one atomic per block
+            }
+            __syncthreads();
+        } else if (lane == 0) {
+            if (p.n_chunks == 1) {
+                if (p.flags & SATMC_ACCUMULATE) p.hits[pair] += cnt; else p.hits[pair] = cnt;
+            } else {
+                atomicAdd(p.hits + pair, (unsigned long long)cnt);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_decide(satmc_pair const* pair, const float* __restrict__ z, uint64_t ldz, int ndof, uint64_t n,
+                         uint8_t* out, uint32_t flags, unsigned long long* exact_evals)
+{
+    __shared__ float s_robot[8];
+    float v[12];
+    DirectSrc src{pair};
+    src.load(0, v);
+    PairConst P;
+    pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
+    if (flags & SATMC_EXACT_ONLY) P.eps = CUDART_INF_F;
+    if (threadIdx.x == 0) exact_robot_corners(v[0], v[1], v[2], v[3], v[4], s_robot);
+    __syncthreads();
+    unsigned long long* ev = (flags & SATMC_EXACT_ONLY) ? nullptr : exact_evals;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float z0 = z[i], z1 = z[ldz + i], z2 = z[2 * ldz + i];
+        unsigned h;
+        if (ndof == 5) h = streamed_sample<5>(P, s_robot, z0, z1, z2, z[3 * ldz + i], z[4 * ldz + i], ev);
+        else           h = streamed_sample<3>(P, s_robot, z0, z1, z2, 0.f, 0.f, ev);
+        out[i] = (uint8_t)h;
+    }
+}
+
+__global__ void k_fused_normals(uint32_t k0, uint32_t k1, uint32_t pid, uint64_t offset, uint64_t n, float* z, uint64_t ldz)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = offset + i;
+        float z0, z1, z2, z3;
+        normals4<true>((uint32_t)s, (uint32_t)(s >> 32), pid, k0, k1, z0, z1, z2, z3);
+        const float z4 = normal5th((uint32_t)s, (uint32_t)(s >> 32), pid, k0, k1);
+        z[i] = z0; z[ldz + i] = z1; z[2 * ldz + i] = z2; z[3 * ldz + i] = z3; z[4 * ldz + i] = z4;
+    }
+}
+
+__global__ void k_philox(const uint32_t* ctr, uint64_t n, uint32_t k0, uint32_t k1, uint32_t* out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[4];
+    philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], k0, k1, w);
+    out[4 * i] = w[0]; out[4 * i + 1] = w[1]; out[4 * i + 2] = w[2]; out[4 * i + 3] = w[3];
+}
+
+__global__ void k_sat_corners(const float* __restrict__ r1, const float* __restrict__ r2, uint64_t n, uint8_t* out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a[8], b[8];
+    const float4* pa = reinterpret_cast<const float4*>(r1 + 8 * i);
+    const float4* pb = reinterpret_cast<const float4*>(r2 + 8 * i);
+    const float4 a0 = __ldg(pa), a1 = __ldg(pa + 1), b0 = __ldg(pb), b1 = __ldg(pb + 1);
+    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+    out[i] = (uint8_t)exact_convex_collide(a, b);
+}
+
+// calcSlack / getBin / done flag of the reference kernel tail (ztest.cu:156-165, utils.cu:186-207).
+// k*k is formed in 64 bits (the reference's int32 product wraps for k > 46340); bins are read in bounds.
+__device__ __forceinline__ float calc_slack(int n, int k)
+{
+    const float z = 1.96;
+    const float alpha = 0.025;
+    if (k == n || k == 0) return (float)(log(1.0 / alpha) / n);
+    const float kk = (float)((long long)k * (long long)k);
+    return z / n * sqrtf((float)k - kk / (float)n);
+}
+
+__global__ void k_ztest_tail(const unsigned long long* __restrict__ hits, float* cps, const float* __restrict__ bins,
+                             const float* __restrict__ bin_acc, int n_bins, int* done, int n_samples, int num_left)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= num_left) return;
+    const int k = (int)cps[g] + (int)hits[g];
+    const float slack = calc_slack(n_samples, k);
+    const float p = (float)k / (float)n_samples;
+    int bin = 0;
+    for (int i = 0; i + 1 < n_bins; i++)
+        if (p >= bins[i] && p <= bins[i + 1]) bin = i;
+    done[g] = (slack <= bin_acc[bin]) ? 1 : 0;
+    cps[g] = (float)k;
+}
+
+__global__ void k_write_cp(float* counts, int n_done, int n_samples)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n_done) counts[g] = counts[g] / (float)n_samples;
+}
+
+__global__ void k_hits_to_cp(const unsigned long long* __restrict__ hits, uint64_t n, uint64_t n_samples, float* cp)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cp[i] = (float)hits[i] / (float)n_samples;
+}
+
+}  // namespace satmc
+
+// =============================================================================================
+// host side / C ABI
+// =============================================================================================
+using namespace satmc;
+
+struct satmc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    int blocks_per_sm = 0;
+    char err[512] = {0};
+    uint64_t launches = 0;
+    unsigned long long* d_exact_evals = nullptr;
+    bool profiling = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    bool last_ms_valid = false;
+    // grow-only device scratch
+    void* d_scratch[3] = {nullptr, nullptr, nullptr};
+    size_t scratch_cap[3] = {0, 0, 0};
+};
+
+static thread_local char g_err[512] = {0};
+
+static int fail(satmc_ctx* ctx, int code, const char* fmt, ...)
+{
+    char* dst = ctx ? ctx->err : g_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail((ctx), SATMC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static int scratch(satmc_ctx* ctx, int slot, size_t bytes, void** out)
+{
+    if (bytes > ctx->scratch_cap[slot]) {
+        if (ctx->d_scratch[slot]) { CU(ctx, cudaFree(ctx->d_scratch[slot])); ctx->d_scratch[slot] = nullptr; ctx->scratch_cap[slot] = 0; }
+        size_t cap = bytes + bytes / 4 + 256;
+        if (cudaMalloc(&ctx->d_scratch[slot], cap) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, SATMC_ERR_NOMEM, "cudaMalloc of %zu bytes failed", cap);
+        }
+        ctx->scratch_cap[slot] = cap;
+    }
+    *out = ctx->d_scratch[slot];
+    return SATMC_OK;
+}
+
+extern "C" {
+
+const char* satmc_version(void) { return "satmc-b200 0.1 (sm_100a)"; }
+
+const char* satmc_last_error(const satmc_ctx* ctx) { return ctx ? ctx->err : g_err; }
+
+int satmc_create(int device, void* stream, satmc_ctx** out)
+{
+    if (!out) return fail(nullptr, SATMC_ERR_INVALID, "satmc_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, SATMC_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+    }
+    if (device < 0 || device >= n) return fail(nullptr, SATMC_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, SATMC_ERR_CUDA, "cudaGetDeviceProperties failed");
+    }
+    if (prop.major != 10)
+        return fail(nullptr, SATMC_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    satmc_ctx* ctx = new (std::nothrow) satmc_ctx();
+    if (!ctx) return fail(nullptr, SATMC_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->stream = (cudaStream_t)stream;
+    ctx->sm_count = prop.multiProcessorCount;
+    DeviceGuard g(device);
+    int bps = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_count<DirectSrc, false>, kThreads, 0);
+    if (e != cudaSuccess || bps < 1) bps = 2;
+    ctx->blocks_per_sm = bps;
+    if (cudaMalloc(&ctx->d_exact_evals, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(ctx->d_exact_evals, 0, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        int rc = fail(nullptr, SATMC_ERR_CUDA, "context allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return SATMC_OK;
+}
+
+int satmc_destroy(satmc_ctx* ctx)
+{
+    if (!ctx) return SATMC_OK;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 3; i++) if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
+    if (ctx->d_exact_evals) cudaFree(ctx->d_exact_evals);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    delete ctx;
+    return SATMC_OK;
+}
+
+int satmc_synchronize(satmc_ctx* ctx)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    DeviceGuard g(ctx->device);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SATMC_OK;
+}
+
+uint64_t satmc_launch_count(const satmc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int satmc_set_profiling(satmc_ctx* ctx, int enabled)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    ctx->profiling = enabled != 0;
+    return SATMC_OK;
+}
+
+float satmc_last_kernel_ms(const satmc_ctx* ctx)
+{
+    if (!ctx || !ctx->last_ms_valid) return -1.0f;
+    satmc_ctx* c = const_cast<satmc_ctx*>(ctx);
+    DeviceGuard g(c->device);
+    if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.0f;
+    return ms;
+}
+
+int satmc_exact_evals(satmc_ctx* ctx, uint64_t* out, int reset)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    DeviceGuard g(ctx->device);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned long long v = 0;
+    CU(ctx, cudaMemcpy(&v, ctx->d_exact_evals, sizeof(v), cudaMemcpyDeviceToHost));
+    if (out) *out = (uint64_t)v;
+    if (reset) CU(ctx, cudaMemset(ctx->d_exact_evals, 0, sizeof(v)));
+    return SATMC_OK;
+}
+
+}  // extern "C"
+
+// Chooses chunking and launches the counting kernel.
+template <class Src, bool STREAMED>
+static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time_it)
+{
+    if (p.n_pairs == 0 || p.n_samples == 0) {
+        if (p.n_pairs && !(p.flags & SATMC_ACCUMULATE))
+            CU(ctx, cudaMemsetAsync(p.hits, 0, p.n_pairs * sizeof(unsigned long long), ctx->stream));
+        return SATMC_OK;
+    }
+    const uint64_t resident_warps = (uint64_t)ctx->sm_count * ctx->blocks_per_sm * kWarps;
+    const uint64_t target_items = resident_warps * 8;             // >= 8 items per resident warp when possible
+    const uint64_t min_chunk = 2048;                              // 64 samples per lane: amortises the pair prologue
+    uint64_t n_chunks = 1;
+    if (p.n_pairs < target_items) {
+        n_chunks = (target_items + p.n_pairs - 1) / p.n_pairs;
+        const uint64_t max_chunks = (p.n_samples + min_chunk - 1) / min_chunk;
+        if (n_chunks > max_chunks) n_chunks = max_chunks;
+        if (n_chunks < 1) n_chunks = 1;
+    }
+    if (n_chunks >= (uint64_t)kWarps) n_chunks = (n_chunks / kWarps) * kWarps;    // block-uniform pairs
+    uint64_t chunk = (p.n_samples + n_chunks - 1) / n_chunks;
+    chunk = ((chunk + 127) / 128) * 128;
+    n_chunks = (p.n_samples + chunk - 1) / chunk;
+    if (n_chunks > 0xffffffffull) return fail(ctx, SATMC_ERR_INVALID, "too many chunks");
+    p.chunk = chunk;
+    p.n_chunks = (uint32_t)n_chunks;
+    p.n_items = p.n_pairs * n_chunks;
+    p.block_uniform = (n_chunks % kWarps == 0) ? 1u : 0u;
+    if (n_chunks > 1 && !(p.flags & SATMC_ACCUMULATE))
+        CU(ctx, cudaMemsetAsync(p.hits, 0, p.n_pairs * sizeof(unsigned long long), ctx->stream));
+    uint64_t blocks = (p.n_items + kWarps - 1) / kWarps;
+    const uint64_t max_blocks = (uint64_t)ctx->sm_count * ctx->blocks_per_sm;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (time_it) CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    k_count<Src, STREAMED><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
+    CU(ctx, cudaGetLastError());
+    if (time_it) { CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream)); ctx->last_ms_valid = true; }
+    ctx->launches++;
+    return SATMC_OK;
+}
+
+static int check_streamed_args(satmc_ctx* ctx, const void* pairs, const void* z, uint64_t ldz, int ndof, uint64_t n_samples,
+                               uint64_t n_pairs, uint64_t z_pair_stride, const void* out)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    if (!pairs || !out) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
+    if (ndof != 3 && ndof != 5) return fail(ctx, SATMC_ERR_INVALID, "ndof must be 3 or 5, got %d", ndof);
+    if (n_samples && !z) return fail(ctx, SATMC_ERR_INVALID, "d_z is NULL");
+    if (n_pairs && n_samples && (n_pairs - 1) * z_pair_stride + n_samples > ldz)
+        return fail(ctx, SATMC_ERR_INVALID, "sample planes too short: need %llu samples per plane, ldz = %llu",
+                    (unsigned long long)((n_pairs - 1) * z_pair_stride + n_samples), (unsigned long long)ldz);
+    return SATMC_OK;
+}
+
+extern "C" {
+
+int satmc_count_fused(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pairs, uint64_t n_samples, uint64_t seed,
+                      uint64_t sample_offset, uint32_t pair_id_offset, uint64_t* d_hits, uint32_t flags)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    if ((!d_pairs || !d_hits) && n_pairs) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
+    if (n_pairs > 0xffffffffull - pair_id_offset) return fail(ctx, SATMC_ERR_INVALID, "pair ids exceed 32 bits");
+    if (((uintptr_t)d_pairs & 15u) != 0) return fail(ctx, SATMC_ERR_INVALID, "d_pairs must be 16-byte aligned");
+    DeviceGuard g(ctx->device);
+    CountParams p{};
+    p.n_pairs = n_pairs; p.n_samples = n_samples; p.sample_offset = sample_offset; p.pair_id_offset = pair_id_offset;
+    p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32); p.flags = flags;
+    p.hits = reinterpret_cast<unsigned long long*>(d_hits); p.exact_evals = ctx->d_exact_evals;
+    return launch_count<DirectSrc, false>(ctx, DirectSrc{d_pairs}, p, ctx->profiling);
+}
+
+int satmc_count_streamed(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pairs, const float* d_z, uint64_t ldz,
+                         uint64_t z_pair_stride, int ndof, uint64_t n_samples, uint64_t* d_hits, uint32_t flags)
+{
+    int rc = check_streamed_args(ctx, d_pairs, d_z, ldz, ndof, n_samples, n_pairs, z_pair_stride, d_hits);
+    if (rc) return rc;
+    if (((uintptr_t)d_pairs & 15u) != 0) return fail(ctx, SATMC_ERR_INVALID, "d_pairs must be 16-byte aligned");
+    DeviceGuard g(ctx->device);
+    CountParams p{};
+    p.n_pairs = n_pairs; p.n_samples = n_samples; p.flags = flags;
+    p.hits = reinterpret_cast<unsigned long long*>(d_hits); p.exact_evals = ctx->d_exact_evals;
+    p.z = d_z; p.ldz = ldz; p.z_pair_stride = z_pair_stride; p.ndof = ndof;
+    p.vec_ok = (((uintptr_t)d_z & 15u) == 0 && ldz % 4 == 0 && z_pair_stride % 4 == 0) ? 1 : 0;
+    return launch_count<DirectSrc, true>(ctx, DirectSrc{d_pairs}, p, ctx->profiling);
+}
+
+int satmc_decide_streamed(satmc_ctx* ctx, const satmc_pair* d_pair, const float* d_z, uint64_t ldz, int ndof,
+                          uint64_t n_samples, uint8_t* d_out, uint32_t flags)
+{
+    int rc = check_streamed_args(ctx, d_pair, d_z, ldz, ndof, n_samples, 1, 0, d_out);
+    if (rc) return rc;
+    if (n_samples == 0) return SATMC_OK;
+    DeviceGuard g(ctx->device);
+    uint64_t blocks = (n_samples + 255) / 256;
+    if (blocks > (uint64_t)ctx->sm_count * 8) blocks = (uint64_t)ctx->sm_count * 8;
+    k_decide<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_pair, d_z, ldz, ndof, n_samples, d_out, flags, ctx->d_exact_evals);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    return SATMC_OK;
+}
+
+int satmc_fused_normals(satmc_ctx* ctx, uint64_t seed, uint32_t pair_id, uint64_t sample_offset, uint64_t n, float* d_z,
+                        uint64_t ldz)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    if (!d_z || ldz < n) return fail(ctx, SATMC_ERR_INVALID, "bad output plane (null or ldz < n)");
+    if (n == 0) return SATMC_OK;
+    DeviceGuard g(ctx->device);
+    uint64_t blocks = (n + 255) / 256;
+    if (blocks > (uint64_t)ctx->sm_count * 8) blocks = (uint64_t)ctx->sm_count * 8;
+    k_fused_normals<<<(unsigned)blocks, 256, 0, ctx->stream>>>((uint32_t)seed, (uint32_t)(seed >> 32), pair_id, sample_offset, n,
+                                                              d_z, ldz);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    return SATMC_OK;
+}
+
+int satmc_philox_blocks(satmc_ctx* ctx, const uint32_t* d_ctr, uint64_t n, uint32_t key0, uint32_t key1, uint32_t* d_out)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    if (!d_ctr || !d_out) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
+    if (n == 0) return SATMC_OK;
+    DeviceGuard g(ctx->device);
+    k_philox<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_ctr, n, key0, key1, d_out);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    return SATMC_OK;
+}
+
+int satmc_sat_corners(satmc_ctx* ctx, const float* d_r1, const float* d_r2, uint64_t n, uint8_t* d_out)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    if (!d_r1 || !d_r2 || !d_out) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
+    if ((((uintptr_t)d_r1 | (uintptr_t)d_r2) & 15u) != 0) return fail(ctx, SATMC_ERR_INVALID, "corner arrays must be 16-byte aligned");
+    if (n == 0) return SATMC_OK;
+    DeviceGuard g(ctx->device);
+    k_sat_corners<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_r1, d_r2, n, d_out);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    return SATMC_OK;
+}
+
+int satmc_mc_step(satmc_ctx* ctx, const float* d_robot_base, const float* d_poses, uint32_t n_poses, const float* d_std_devs,
+                  uint32_t n_std, const float* d_pose_idxs, const float* d_std_dev_idxs, const float* d_positions,
+                  float* d_cps, const float* d_accuracy_bins, const float* d_bin_accuracy, int n_accuracy_bins,
+                  int* d_done, int iteration, int n_samples, int n_batch, int num_left, uint64_t seed,
+                  uint32_t stream_id_offset)
+{
+    (void)iteration;
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    if (!d_robot_base || !d_poses || !d_std_devs || !d_pose_idxs || !d_std_dev_idxs || !d_positions || !d_cps ||
+        !d_accuracy_bins || !d_bin_accuracy || !d_done)
+        return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
+    if (n_batch < 0 || n_samples < n_batch || num_left < 0 || n_accuracy_bins < 2 || n_poses == 0 || n_std == 0)
+        return fail(ctx, SATMC_ERR_INVALID, "bad sizes (n_batch %d, n_samples %d, num_left %d, bins %d)", n_batch, n_samples,
+                    num_left, n_accuracy_bins);
+    if (num_left == 0) return SATMC_OK;
+    DeviceGuard g(ctx->device);
+    void* d_hits = nullptr;
+    int rc = scratch(ctx, 0, (size_t)num_left * sizeof(unsigned long long), &d_hits);
+    if (rc) return rc;
+    CountParams p{};
+    p.n_pairs = (uint64_t)num_left; p.n_samples = (uint64_t)n_batch; p.sample_offset = (uint64_t)(n_samples - n_batch);
+    p.pair_id_offset = stream_id_offset; p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32); p.flags = 0;
+    p.hits = reinterpret_cast<unsigned long long*>(d_hits); p.exact_evals = ctx->d_exact_evals;
+    IndirectSrc src{d_robot_base, d_poses, d_std_devs, d_pose_idxs, d_std_dev_idxs, d_positions, n_poses, n_std};
+    if (n_batch == 0) CU(ctx, cudaMemsetAsync(d_hits, 0, (size_t)num_left * sizeof(unsigned long long), ctx->stream));
+    rc = launch_count<IndirectSrc, false>(ctx, src, p, ctx->profiling);
+    if (rc) return rc;
+    k_ztest_tail<<<(num_left + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<unsigned long long*>(d_hits), d_cps,
+                                                                   d_accuracy_bins, d_bin_accuracy, n_accuracy_bins, d_done,
+                                                                   n_samples, num_left);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    return SATMC_OK;
+}
+
+int satmc_write_collision_probability(satmc_ctx* ctx, float* d_counts, int n_done, int n_samples)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    if (!d_counts && n_done) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
+    if (n_done <= 0) return SATMC_OK;
+    DeviceGuard g(ctx->device);
+    k_write_cp<<<(n_done + 255) / 256, 256, 0, ctx->stream>>>(d_counts, n_done, n_samples);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    return SATMC_OK;
+}
+
+// ---- host-buffer variants ---------------------------------------------------------------------
+
+int satmc_count_fused_host(satmc_ctx* ctx, const satmc_pair* h_pairs, uint64_t n_pairs, uint64_t n_samples, uint64_t seed,
+                           uint64_t sample_offset, uint32_t pair_id_offset, uint64_t* h_hits, uint32_t flags)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    if ((!h_pairs || !h_hits) && n_pairs) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
+    if (n_pairs == 0) return SATMC_OK;
+    DeviceGuard g(ctx->device);
+    void *d_pairs = nullptr, *d_hits = nullptr;
+    int rc = scratch(ctx, 1, n_pairs * sizeof(satmc_pair), &d_pairs); if (rc) return rc;
+    rc = scratch(ctx, 2, n_pairs * sizeof(uint64_t), &d_hits); if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(d_pairs, h_pairs, n_pairs * sizeof(satmc_pair), cudaMemcpyHostToDevice, ctx->stream));
+    if (flags & SATMC_ACCUMULATE)
+        CU(ctx, cudaMemcpyAsync(d_hits, h_hits, n_pairs * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    const bool prof = ctx->profiling; ctx->profiling = true;
+    rc = satmc_count_fused(ctx, (const satmc_pair*)d_pairs, n_pairs, n_samples, seed, sample_offset, pair_id_offset,
+                           (uint64_t*)d_hits, flags);
+    ctx->profiling = prof;
+    if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(h_hits, d_hits, n_pairs * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SATMC_OK;
+}
+
+int satmc_count_streamed_host(satmc_ctx* ctx, const satmc_pair* h_pairs, uint64_t n_pairs, const float* h_z, uint64_t ldz,
+                              uint64_t z_pair_stride, int ndof, uint64_t n_samples, uint64_t* h_hits, uint32_t flags)
+{
+    int rc = check_streamed_args(ctx, h_pairs, h_z, ldz, ndof, n_samples, n_pairs, z_pair_stride, h_hits);
+    if (rc) return rc;
+    if (n_pairs == 0) return SATMC_OK;
+    DeviceGuard g(ctx->device);
+    void *d_pairs = nullptr, *d_hits = nullptr, *d_z = nullptr;
+    const uint64_t ldz_dev = (ldz + 3) / 4 * 4;
+    rc = scratch(ctx, 1, n_pairs * sizeof(satmc_pair), &d_pairs); if (rc) return rc;
+    rc = scratch(ctx, 2, n_pairs * sizeof(uint64_t), &d_hits); if (rc) return rc;
+    rc = scratch(ctx, 0, (size_t)ndof * ldz_dev * sizeof(float), &d_z); if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(d_pairs, h_pairs, n_pairs * sizeof(satmc_pair), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpy2DAsync(d_z, ldz_dev * sizeof(float), h_z, ldz * sizeof(float), ldz * sizeof(float), (size_t)ndof,
+                              cudaMemcpyHostToDevice, ctx->stream));
+    if (flags & SATMC_ACCUMULATE)
+        CU(ctx, cudaMemcpyAsync(d_hits, h_hits, n_pairs * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    const bool prof = ctx->profiling; ctx->profiling = true;
+    rc = satmc_count_streamed(ctx, (const satmc_pair*)d_pairs, n_pairs, (const float*)d_z, ldz_dev, z_pair_stride, ndof,
+                              n_samples, (uint64_t*)d_hits, flags);
+    ctx->profiling = prof;
+    if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(h_hits, d_hits, n_pairs * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SATMC_OK;
+}
+
+int satmc_collision_probability_host(satmc_ctx* ctx, const satmc_pair* h_pairs, uint64_t n_pairs, uint64_t n_samples,
+                                     uint64_t seed, float* h_cp)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    if ((!h_pairs || !h_cp) && n_pairs) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
+    if (n_samples == 0) return fail(ctx, SATMC_ERR_INVALID, "n_samples must be > 0");
+    if (n_pairs == 0) return SATMC_OK;
+    DeviceGuard g(ctx->device);
+    void *d_pairs = nullptr, *d_hits = nullptr, *d_cp = nullptr;
+    int rc = scratch(ctx, 1, n_pairs * sizeof(satmc_pair), &d_pairs); if (rc) return rc;
+    rc = scratch(ctx, 2, n_pairs * sizeof(uint64_t), &d_hits); if (rc) return rc;
+    rc = scratch(ctx, 0, n_pairs * sizeof(float), &d_cp); if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(d_pairs, h_pairs, n_pairs * sizeof(satmc_pair), cudaMemcpyHostToDevice, ctx->stream));
+    const bool prof = ctx->profiling; ctx->profiling = true;
+    rc = satmc_count_fused(ctx, (const satmc_pair*)d_pairs, n_pairs, n_samples, seed, 0, 0, (uint64_t*)d_hits, 0);
+    ctx->profiling = prof;
+    if (rc) return rc;
+    k_hits_to_cp<<<(unsigned)((n_pairs + 255) / 256), 256, 0, ctx->stream>>>((const unsigned long long*)d_hits, n_pairs, n_samples,
+                                                                           (float*)d_cp);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    CU(ctx, cudaMemcpyAsync(h_cp, d_cp, n_pairs * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SATMC_OK;
+}
+
+int satmc_host_alloc(void** out, size_t bytes)
+{
+    if (!out) return fail(nullptr, SATMC_ERR_INVALID, "out is NULL");
+    if (cudaMallocHost(out, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return fail(nullptr, SATMC_ERR_NOMEM, "cudaMallocHost of %zu bytes failed", bytes);
+    }
+    return SATMC_OK;
+}
+
+int satmc_host_free(void* p)
+{
+    if (p && cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, SATMC_ERR_CUDA, "cudaFreeHost failed"); }
+    return SATMC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,212 @@
+// satmc_geom.cuh -- device geometry for the Monte Carlo SAT path (sm_100a).
+//
+// Two evaluators of the same decision "does the sampled obstacle overlap the robot?":
+//
+//   exact_*  : the reference arithmetic, operation for operation, as nvcc 12.9 compiles
+//              sample_rectangle (utils.cu:144-157) and convex_collide (utils.cu:159-184) inside the
+//              reference kernel (ztest.cu:151-155).  Every rounding is pinned with
+//              __fmaf_rn/__fmul_rn/__fadd_rn so the compiler can neither add nor remove a
+//              contraction.  This is the arithmetic contract of the library.
+//
+//   screen_* : a ~35-instruction oriented-box separating-axis test in centre/half-extent form
+//              (4 axes, approximate sin/cos) that returns the largest normalised signed gap m.
+//              |m| > eps  => the sign of m provably equals the exact decision (DESIGN.md section 4
+//              derives eps); otherwise the sample is re-evaluated with exact_*.  Results are
+//              therefore bit-identical to the exact path for every input, including NaN/Inf.
+//
+// Compile WITHOUT --use_fast_math: cosf/sinf below must be the precise libdevice versions the
+// reference calls (utils.cu:133-134).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math_constants.h>
+
+namespace satmc {
+
+// Bound on |z| under which the screening threshold is valid.  The fused sampler cannot exceed 6.77
+// (Box-Muller radius of the smallest uniform); streamed samples are checked against it.
+#define SATMC_Z_BOUND 8.0f
+
+// ---------------------------------------------------------------------------------------------
+// exact reference arithmetic
+// ---------------------------------------------------------------------------------------------
+
+// create_rect(w,h) [utils.cu:119-130] + rot_trans_rectangle(pos, theta) [utils.cu:132-142] for the
+// robot (ztest.cu:148-149,297):  x' = FADD(FFMA(x,c,-FMUL(y,s)), px)   y' = FADD(FFMA(x,s,FMUL(y,c)), py)
+__device__ __forceinline__ void exact_robot_corners(float px, float py, float theta, float rw, float rh,
+                                                    float r[8])
+{
+    const float hx = rw / 2, hy = rh / 2;
+    const float c = cosf(theta), s = sinf(theta);
+    const float bx[4] = {-hx, hx, hx, -hx};
+    const float by[4] = {-hy, -hy, hy, hy};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        r[2 * i]     = __fadd_rn(__fmaf_rn(bx[i], c, -__fmul_rn(by[i], s)), px);
+        r[2 * i + 1] = __fadd_rn(__fmaf_rn(bx[i], s, __fmul_rn(by[i], c)), py);
+    }
+}
+
+// sample_rectangle with the normals supplied, as compiled inside the reference kernel:
+//   dt = FMUL(z2,sd_t)  dw = FMUL(z3,sd_w)  dh = FMUL(z4,sd_h)   q = FFMA(dw|dh, -+0.5, base)
+//   x' = FFMA(z0, sd_x, FFMA(qx, c, -FMUL(qy, s)))   y' = FFMA(z1, sd_y, FFMA(qx, s, FMUL(qy, c)))
+__device__ __forceinline__ void exact_sample_corners(float ow, float oh, float sd_x, float sd_y, float sd_t,
+                                                     float sd_w, float sd_h, float z0, float z1, float z2,
+                                                     float z3, float z4, float o[8])
+{
+    const float hx = ow / 2, hy = oh / 2;
+    const float dt = __fmul_rn(z2, sd_t);
+    const float dw = __fmul_rn(z3, sd_w);
+    const float dh = __fmul_rn(z4, sd_h);
+    const float c = cosf(dt), s = sinf(dt);
+    const float bx[4] = {-hx, hx, hx, -hx};
+    const float by[4] = {-hy, -hy, hy, hy};
+    const float hs_x[4] = {-0.5f, 0.5f, 0.5f, -0.5f};
+    const float hs_y[4] = {-0.5f, -0.5f, 0.5f, 0.5f};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float qx = __fmaf_rn(dw, hs_x[i], bx[i]);
+        const float qy = __fmaf_rn(dh, hs_y[i], by[i]);
+        o[2 * i]     = __fmaf_rn(z0, sd_x, __fmaf_rn(qx, c, -__fmul_rn(qy, s)));
+        o[2 * i + 1] = __fmaf_rn(z1, sd_y, __fmaf_rn(qx, s, __fmul_rn(qy, c)));
+    }
+}
+
+// convex_collide [utils.cu:159-184]: 8 axes (edge vectors of r1 then r2),
+//   n = FADD(r[i+1], -r[i])   p(q) = FFMA(n0, q.x, FMUL(n1, q.y))
+// min/max with thrust's sequential minmax_element semantics (strict <, element 0 seeds both; NaNs
+// never replace), strict separation test, no early exit.
+__device__ __forceinline__ int exact_convex_collide(const float r1[8], const float r2[8])
+{
+    int collide = 1;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const float* r = j ? r2 : r1;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float n0 = __fadd_rn(r[((i + 1) * 2) % 8], -r[i * 2]);
+            const float n1 = __fadd_rn(r[((i + 1) * 2 + 1) % 8], -r[i * 2 + 1]);
+            float min1, max1, min2, max2;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float p1 = __fmaf_rn(n0, r1[2 * k], __fmul_rn(n1, r1[2 * k + 1]));
+                const float p2 = __fmaf_rn(n0, r2[2 * k], __fmul_rn(n1, r2[2 * k + 1]));
+                if (k == 0) { min1 = max1 = p1; min2 = max2 = p2; }
+                else {
+                    if (p1 < min1) min1 = p1;
+                    if (max1 < p1) max1 = p1;
+                    if (p2 < min2) min2 = p2;
+                    if (max2 < p2) max2 = p2;
+                }
+            }
+            if (max1 < min2 || max2 < min1) collide = 0;
+        }
+    }
+    return collide;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-pair constants
+// ---------------------------------------------------------------------------------------------
+struct PairConst {
+    // screening pass (robot: centre P, axes A0=(ca,sa), A1=(-sa,ca), half extents a0,a1;
+    //                 obstacle: centre (sd_x z0, sd_y z1), angle sd_t z2, half extents b0,b1)
+    float px, py, nsx, nsy;          // u = P - d :  ux = fma(nsx, z0, px)
+    float pa0, pa1;                  // P.A0, P.A1
+    float nkx0, nky0, kx1, nky1;     // u.A0 = pa0 + nkx0 z0 + nky0 z1 ; u.A1 = pa1 + kx1 z0 + nky1 z1
+    float ca, sa;
+    float a0, a1, b0, b1;
+    float hw, hh;                    // 0.5*sd_w, 0.5*sd_h  (5-DoF half-extent perturbation)
+    float eps;                       // screening threshold; +inf => always exact
+    // exact pass
+    float ow, oh, sd_x, sd_y, sd_t, sd_w, sd_h;
+};
+
+// Screening threshold eps.  u = 2^-24.  All quantities are upper bounds over
+// every sample with |z_k| <= SATMC_Z_BOUND:
+//   E_ref  : |exact-arithmetic normalised gap of the reference's rounded quads on its rounded edge
+//             axis  -  gap of the ideal rectangles on the ideal axis|
+//   E_fast : |screening value  -  gap of the ideal rectangles|
+__device__ __forceinline__ float screen_eps(float px, float py, float a0, float a1, float b0, float b1,
+                                            float sd_x, float sd_y, float sd_t, float sd_w, float sd_h)
+{
+    const float u = 5.9604645e-8f;
+    const float Z = SATMC_Z_BOUND;
+    const float dmx = Z * fabsf(sd_x), dmy = Z * fabsf(sd_y), dmt = Z * fabsf(sd_t);
+    const float dmw = 0.5f * Z * fabsf(sd_w), dmh = 0.5f * Z * fabsf(sd_h);
+    const float hx_max = b0 + dmw, hy_max = b1 + dmh;
+    const float hx_min = b0 - dmw, hy_min = b1 - dmh;
+    const float r1a = a0 + a1, r1b = hx_max + hy_max;
+    const float pn = fabsf(px) + fabsf(py), dn = dmx + dmy;
+    const float un = pn + dn;
+    const float M = un + r1a + r1b;
+    const float dS = u * (7.0f * r1b + fmaxf(dmx, dmy));
+    const float dR = u * (7.0f * r1a + pn);
+    const float LB = 2.0f * fminf(hx_min, hy_min);
+    const float LA = 2.0f * fminf(a0, a1);
+    const float e_ref = 5.5f * u * M + 1.5f * (dS + dR) + 3.0f * M * fmaxf(dS / LB, dR / LA);
+    const float e_m = 9.5367432e-7f + 4.0f * u * dmt;                 // |__sinf/__cosf - sin/cos|, |x| <= dmt
+    const float e_fast = (un + 2.0f * (r1a + r1b)) * e_m + 24.0f * u * M;
+    float eps = 1.0625f * (e_ref + e_fast);
+    // outside the validated domain of the bound: degenerate or flipped rectangles, huge angles,
+    // non-finite input -> never trust the screening pass
+    const bool ok = (LB > 0.0f) && (LA > 0.0f) && (dmt <= 64.0f) && (eps == eps) && (M < 1.0e18f);
+    return ok ? eps : CUDART_INF_F;
+}
+
+__device__ __forceinline__ void pair_const_init(PairConst& P, float rx, float ry, float rtheta, float rw,
+                                                float rh, float ow, float oh, float sd_x, float sd_y,
+                                                float sd_t, float sd_w, float sd_h)
+{
+    const float ca = cosf(rtheta), sa = sinf(rtheta);
+    P.px = rx; P.py = ry; P.nsx = -sd_x; P.nsy = -sd_y;
+    P.ca = ca; P.sa = sa;
+    P.pa0 = fmaf(rx, ca, ry * sa);
+    P.pa1 = fmaf(ry, ca, -(rx * sa));
+    P.nkx0 = -(sd_x * ca); P.nky0 = -(sd_y * sa);
+    P.kx1 = sd_x * sa;     P.nky1 = -(sd_y * ca);
+    P.a0 = 0.5f * fabsf(rw); P.a1 = 0.5f * fabsf(rh);
+    P.b0 = 0.5f * ow;        P.b1 = 0.5f * oh;
+    P.hw = 0.5f * sd_w;      P.hh = 0.5f * sd_h;
+    P.ow = ow; P.oh = oh; P.sd_x = sd_x; P.sd_y = sd_y; P.sd_t = sd_t; P.sd_w = sd_w; P.sd_h = sd_h;
+    P.eps = screen_eps(rx, ry, P.a0, P.a1, P.b0, P.b1, sd_x, sd_y, sd_t, sd_w, sd_h);
+}
+
+// ---------------------------------------------------------------------------------------------
+// screening pass: largest normalised signed gap over the 4 box axes (m > 0 separated, m < 0 overlap)
+// ---------------------------------------------------------------------------------------------
+template <int NDOF>
+__device__ __forceinline__ float screen_gap(const PairConst& P, float z0, float z1, float z2, float z3, float z4)
+{
+    const float dt = __fmul_rn(z2, P.sd_t);              // the same float the exact pass feeds to sinf/cosf
+    const float s = __sinf(dt), c = __cosf(dt);
+    const float ux = fmaf(P.nsx, z0, P.px);
+    const float uy = fmaf(P.nsy, z1, P.py);
+    const float ub0 = fmaf(ux, c, uy * s);
+    const float ub1 = fmaf(uy, c, -(ux * s));
+    const float ua0 = fmaf(P.nkx0, z0, fmaf(P.nky0, z1, P.pa0));
+    const float ua1 = fmaf(P.kx1, z0, fmaf(P.nky1, z1, P.pa1));
+    const float C = fabsf(fmaf(P.ca, c, P.sa * s));
+    const float S = fabsf(fmaf(P.sa, c, -(P.ca * s)));
+    float hx = P.b0, hy = P.b1;
+    if (NDOF == 5) { hx = fmaf(z3, P.hw, hx); hy = fmaf(z4, P.hh, hy); }
+    const float tb0 = fabsf(ub0) - fmaf(P.a0, C, fmaf(P.a1, S, hx));
+    const float tb1 = fabsf(ub1) - fmaf(P.a0, S, fmaf(P.a1, C, hy));
+    const float ta0 = fabsf(ua0) - fmaf(hx, C, fmaf(hy, S, P.a0));
+    const float ta1 = fabsf(ua1) - fmaf(hx, S, fmaf(hy, C, P.a1));
+    return fmaxf(fmaxf(tb0, tb1), fmaxf(ta0, ta1));
+}
+
+// Exact decision for one sample given the robot corners (kept in shared memory by the caller).
+__device__ __noinline__ int exact_decide(const float* __restrict__ robot, float ow, float oh, float sd_x, float sd_y,
+                                         float sd_t, float sd_w, float sd_h, float z0, float z1, float z2,
+                                         float z3, float z4)
+{
+    float r[8], o[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) r[k] = robot[k];
+    exact_sample_corners(ow, oh, sd_x, sd_y, sd_t, sd_w, sd_h, z0, z1, z2, z3, z4, o);
+    return exact_convex_collide(r, o);
+}
+
+}  // namespace satmc

@@ -1,0 +1,180 @@
+/*
+ * satmc.h -- C ABI of the B200-native Monte Carlo SAT collision-probability path.
+ *
+ * Drop-in boundary for the one hot path of beautifulv0id/Convex-2D-GPU-Collision-Detection:
+ * "for each (robot rectangle, Gaussian-uncertain obstacle rectangle) pair draw N perturbed obstacle
+ * poses, run the separating-axis test on each, count the hits".  The reference has no library API;
+ * its three programs launch one kernel, so every entry point below names the reference code it
+ * replaces (paths relative to the reference repository root).  INTEGRATION.md shows the edit a
+ * reference maintainer makes in each main().
+ *
+ * Conventions
+ *   - plain C, no CUDA/torch types: device pointers are `void*`-compatible raw addresses, the
+ *     stream is passed as `void*` (a cudaStream_t) at context creation.
+ *   - every function returns SATMC_OK (0) or a negative satmc_status; nothing inside the library
+ *     calls exit() (the reference's gpuAssert does, utils.cu:59-67).  satmc_last_error() gives text.
+ *   - "d_" parameters are device pointers on the context's device, "h_" are host pointers.
+ *     The *_host variants copy H2D/D2H on the context's stream and synchronise it before returning.
+ *   - all work is enqueued on the context's stream; device-pointer entry points are asynchronous.
+ *   - one context per host thread / per GPU; contexts share no state.
+ *   - there is no CPU fallback: with no usable sm_100 device satmc_create() fails with
+ *     SATMC_ERR_NO_DEVICE.
+ *
+ * Arithmetic contract: for given normals z the collide decision of every
+ * sample is bit-identical to what the reference's compiled kernel (nvcc 12.9, default flags,
+ * sm_100a) decides: sample_rectangle utils.cu:144-157 -> convex_collide utils.cu:159-184, 8 axes,
+ * strict <, NaN => collide.
+ */
+#ifndef SATMC_H
+#define SATMC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SATMC_VERSION_MAJOR 0
+#define SATMC_VERSION_MINOR 1
+
+typedef enum {
+    SATMC_OK              =  0,
+    SATMC_ERR_INVALID     = -1,   /* bad argument (null pointer, ndof not 3/5, misaligned ...)      */
+    SATMC_ERR_NO_DEVICE   = -2,   /* no CUDA device / not compute capability 10.x                    */
+    SATMC_ERR_CUDA        = -3,   /* a CUDA runtime call failed; see satmc_last_error()              */
+    SATMC_ERR_NOMEM       = -4    /* host or device allocation failed                                */
+} satmc_status;
+
+/* One (robot, uncertain obstacle) pair in direct form: 12 packed float32 = 48 bytes.
+ * Coordinates are in the obstacle's nominal frame, as in the reference: the obstacle is an
+ * ow x oh rectangle centred at the origin with heading 0 (create_rect, ztest.cu:143-144), the robot
+ * an rw x rh rectangle with heading rtheta centred at (rx, ry) (ztest.cu:148-149,297).
+ * sd_* are the STANDARD DEVIATIONS of the obstacle pose/shape perturbation (StdDev, utils.cu:86-89,
+ * 107; the .npy files hold variances, the reference takes sqrt at load, ztest.cu:245-251). */
+typedef struct satmc_pair {
+    float rx, ry;        /* Position            utils.cu:74-77   */
+    float rtheta;        /* Pose.theta          utils.cu:91-94   */
+    float rw, rh;        /* --robot_width / --robot_height, defaults 4.07 x 1.74 */
+    float ow, oh;        /* Pose.width / .height                 */
+    float sd_x, sd_y, sd_theta, sd_w, sd_h;
+} satmc_pair;
+
+typedef struct satmc_ctx satmc_ctx;
+
+/* Flags for the counting entry points. */
+#define SATMC_ACCUMULATE  0x1u   /* add to d_hits instead of overwriting it                          */
+#define SATMC_EXACT_ONLY  0x2u   /* evaluate every sample with the exact 8-axis reference arithmetic */
+                                 /* (no screening pass); same results, used for A/B verification     */
+
+/* ---- context ------------------------------------------------------------------------------- */
+
+/* Creates a context on CUDA device `device`, enqueueing on `stream` (a cudaStream_t cast to void*;
+ * NULL = the legacy default stream, which is what the reference uses throughout). */
+int satmc_create(int device, void* stream, satmc_ctx** out);
+int satmc_destroy(satmc_ctx* ctx);
+/* Blocks until everything enqueued through `ctx` has finished. */
+int satmc_synchronize(satmc_ctx* ctx);
+/* Text of the last error on this context ("" if none); never NULL.  ctx may be NULL. */
+const char* satmc_last_error(const satmc_ctx* ctx);
+const char* satmc_version(void);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches claim). */
+uint64_t satmc_launch_count(const satmc_ctx* ctx);
+/* Time in milliseconds the device spent in the most recent counting kernel launched by a *_host
+ * call or by a call made while profiling is enabled (CUDA events on the context's stream). */
+int satmc_set_profiling(satmc_ctx* ctx, int enabled);
+float satmc_last_kernel_ms(const satmc_ctx* ctx);
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+
+/* Fused path: counter-based Philox4x32-10 -> Box-Muller normals -> perturbed obstacle -> SAT ->
+ * hit count, samples never touch HBM.
+ *   replaces: setup_kernel utils.cu:111-117 + the sample loop of
+ *             monte_carlo_sample_collision_dataset_uniform ztest.cu:151-155
+ *             (= compute_collision_probability.cu:135-139, generate_dataset.cu:238-242)
+ * d_hits[i] = #{ s in [sample_offset, sample_offset + n_samples) : pair i collides on sample s }.
+ * The normals of sample s of pair i depend only on (seed, pair_id_offset + i, s): any split of the
+ * pair range or the sample range over calls, streams, GPUs or ranks gives bit-identical totals.
+ * Pairs with sd_w == sd_h == 0 take a 3-normal path (x, y, theta), others draw all five. */
+int satmc_count_fused(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pairs,
+                      uint64_t n_samples, uint64_t seed, uint64_t sample_offset,
+                      uint32_t pair_id_offset, uint64_t* d_hits, uint32_t flags);
+
+/* Streamed path: the normals are supplied by the caller (verification against the reference on
+ * shared samples; HBM-bound).  d_z is SoA: plane k (k = 0..ndof-1 = x, y, theta[, w, h]) of sample
+ * s is d_z[k*ldz + s].  Pair i consumes samples [i*z_pair_stride, i*z_pair_stride + n_samples) of
+ * every plane (z_pair_stride = 0: all pairs share one bank -- common random numbers).  ndof = 3
+ * treats dw = dh = 0.  Fastest when d_z is 16-byte aligned and ldz, z_pair_stride are multiples of 4. */
+int satmc_count_streamed(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pairs,
+                         const float* d_z, uint64_t ldz, uint64_t z_pair_stride, int ndof,
+                         uint64_t n_samples, uint64_t* d_hits, uint32_t flags);
+
+/* Per-sample decisions of ONE pair on supplied normals: d_out[s] = 1 collide / 0 separated.
+ * (what `n_samplestrue += convex_collide(...)` adds at ztest.cu:154, sample by sample) */
+int satmc_decide_streamed(satmc_ctx* ctx, const satmc_pair* d_pair, const float* d_z, uint64_t ldz,
+                          int ndof, uint64_t n_samples, uint8_t* d_out, uint32_t flags);
+
+/* The normals the fused path uses for samples [sample_offset, sample_offset+n) of pair `pair_id`,
+ * written as 5 SoA planes d_z[k*ldz + s].  Feeding them to satmc_count_streamed / the oracle must
+ * reproduce satmc_count_fused's count exactly. */
+int satmc_fused_normals(satmc_ctx* ctx, uint64_t seed, uint32_t pair_id, uint64_t sample_offset,
+                        uint64_t n, float* d_z, uint64_t ldz);
+
+/* Raw Philox4x32-10 blocks (known-answer tests): d_out[4*i..4*i+3] = philox(ctr = d_ctr[4*i..], key). */
+int satmc_philox_blocks(satmc_ctx* ctx, const uint32_t* d_ctr, uint64_t n, uint32_t key0, uint32_t key1,
+                        uint32_t* d_out);
+
+/* SAT on explicit corner sets (AoS x0,y0..x3,y3, [n][8] each): d_out[i] = convex_collide(r1_i, r2_i).
+ *   replaces: convex_collide utils.cu:159-184 (BASELINE config 1 on the GPU) */
+int satmc_sat_corners(satmc_ctx* ctx, const float* d_r1, const float* d_r2, uint64_t n, uint8_t* d_out);
+
+/* Diagnostics: number of samples that the screening pass could not decide and that were re-evaluated
+ * with the exact arithmetic, accumulated over all counting calls since the last reset. */
+int satmc_exact_evals(satmc_ctx* ctx, uint64_t* out, int reset);
+
+/* ---- reference-compatible Monte Carlo step ------------------------------------------------- */
+
+/* One launch of the reference kernel, same argument meaning as
+ *   monte_carlo_sample_collision_dataset_uniform  ztest.cu:106-121
+ *   (= compute_collision_probability.cu:90-105; generate_dataset.cu:175-194 without its iteration-0
+ *   position sampling, which satmc_sample_positions provides)
+ * d_robot_base: 8 floats from create_rect(robot_w, robot_h); d_poses: [n_poses][3] (width, height,
+ * theta); d_std_devs: [n_std][5]; d_pose_idxs / d_std_dev_idxs: float indices per live pair;
+ * d_positions: [num_left][2]; d_cps: running hit COUNT as float, in/out (ztest.cu:135,165);
+ * d_accuracy_bins [n_accuracy_bins], d_bin_accuracy [n_accuracy_bins-1]; d_done: out flags.
+ * n_samples = cumulative samples AFTER this step, n_batch = samples added now, first num_left
+ * entries are live.  The curandState* of the reference is replaced by (seed, stream_id_offset):
+ * pair g draws the Philox stream of id stream_id_offset + g at sample indices
+ * [n_samples - n_batch, n_samples).  Out-of-range bin reads of the reference (utils.cu:202) are not
+ * replicated: the last bin edge is treated as closed and nothing is read past the arrays. */
+int satmc_mc_step(satmc_ctx* ctx, const float* d_robot_base, const float* d_poses, uint32_t n_poses,
+                  const float* d_std_devs, uint32_t n_std, const float* d_pose_idxs,
+                  const float* d_std_dev_idxs, const float* d_positions, float* d_cps,
+                  const float* d_accuracy_bins, const float* d_bin_accuracy, int n_accuracy_bins,
+                  int* d_done, int iteration, int n_samples, int n_batch, int num_left,
+                  uint64_t seed, uint32_t stream_id_offset);
+
+/* count -> probability on a finished tail.   replaces: write_collision_probability utils.cu:210-215 */
+int satmc_write_collision_probability(satmc_ctx* ctx, float* d_counts, int n_done, int n_samples);
+
+/* ---- host-buffer convenience (H2D + kernel + D2H inside the call) --------------------------- */
+
+int satmc_count_fused_host(satmc_ctx* ctx, const satmc_pair* h_pairs, uint64_t n_pairs,
+                           uint64_t n_samples, uint64_t seed, uint64_t sample_offset,
+                           uint32_t pair_id_offset, uint64_t* h_hits, uint32_t flags);
+int satmc_count_streamed_host(satmc_ctx* ctx, const satmc_pair* h_pairs, uint64_t n_pairs,
+                              const float* h_z, uint64_t ldz, uint64_t z_pair_stride, int ndof,
+                              uint64_t n_samples, uint64_t* h_hits, uint32_t flags);
+/* probabilities = hits / n_samples as float32 (the `cp` column of the dataset rows,
+ * generate_dataset.cu:485-494) */
+int satmc_collision_probability_host(satmc_ctx* ctx, const satmc_pair* h_pairs, uint64_t n_pairs,
+                                     uint64_t n_samples, uint64_t seed, float* h_cp);
+
+/* Pinned host memory for the *_host paths (optional; pageable memory works, slower). */
+int satmc_host_alloc(void** out, size_t bytes);
+int satmc_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SATMC_H */

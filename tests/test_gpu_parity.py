@@ -1,0 +1,373 @@
+"""GPU box: the CUDA path (through the C ABI) against the oracle and the compiled reference.
+
+Bar: bit-exact for every decision and hit count on shared samples; binomial bounds (stated in each
+test) for the native RNG.
+"""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+EXACT = 0x2      # SATMC_EXACT_ONLY
+ACC = 0x1        # SATMC_ACCUMULATE
+
+
+def streamed(ctx, dev, pairs, z, n=None, z_pair_stride=0, flags=0, misalign=False):
+    ndof, ldz = z.shape
+    if misalign:                                  # odd leading dimension + offset base: scalar-load path
+        zz = np.zeros((ndof, ldz + 3), np.float32); zz[:, 1:1 + ldz] = z
+        d_all = dev.put(zz.ravel())
+        d_z = d_all[1:]
+        ldz_dev = ldz + 3
+    else:
+        d_z = dev.put(z.ravel()); ldz_dev = ldz
+    n = ldz if n is None else n
+    d_pairs = dev.put(pairs)
+    d_hits = dev.zeros(pairs.size, np.uint64)
+    ctx.count_streamed(d_pairs, pairs.size, d_z, ldz_dev, ndof, n, d_hits, z_pair_stride=z_pair_stride, flags=flags)
+    ctx.synchronize()
+    return dev.get(d_hits, np.uint64)
+
+
+def fused(ctx, dev, pairs, n, seed, sample_offset=0, pair_id_offset=0, flags=0, d_hits=None):
+    d_pairs = dev.put(pairs)
+    if d_hits is None:
+        d_hits = dev.zeros(pairs.size, np.uint64)
+    ctx.count_fused(d_pairs, pairs.size, n, seed, d_hits, sample_offset=sample_offset, pair_id_offset=pair_id_offset, flags=flags)
+    ctx.synchronize()
+    return dev.get(d_hits, np.uint64)
+
+
+# ---- SAT on explicit corners (config 1 on the GPU) --------------------------------------------------
+def test_sat_corners_bit_exact(ctx, dev, oracle, refgpu, workloads):
+    r1, r2 = workloads.cfg1_rect_pairs(10_000, seed=1)
+    d_out = dev.zeros(r1.shape[0], np.uint8)
+    ctx.sat_corners(dev.put(r1.ravel()), dev.put(r2.ravel()), r1.shape[0], d_out)
+    got = dev.get(d_out)
+    np.testing.assert_array_equal(got, oracle.sat_batch(r1, r2))
+    np.testing.assert_array_equal(got, refgpu.convex_collide(r1, r2).astype(np.uint8))
+
+
+def test_sat_corners_nonfinite_and_touching(ctx, dev, refgpu):
+    base = np.array([-1, -1, 1, -1, 1, 1, -1, 1], np.float32)
+    r1 = np.stack([base] * 6)
+    r2 = np.stack([base + np.float32(2) * np.tile([1, 0], 4).astype(np.float32),        # touching
+                   np.full(8, np.nan, np.float32), base + np.float32(np.inf), base * 0,
+                   np.array([3, -1, np.nan, -1, 5, 1, 3, 1], np.float32), base + np.float32(5)])
+    d_out = dev.zeros(6, np.uint8)
+    ctx.sat_corners(dev.put(r1.ravel()), dev.put(r2.ravel()), 6, d_out)
+    np.testing.assert_array_equal(dev.get(d_out), refgpu.convex_collide(r1, r2).astype(np.uint8))
+
+
+# ---- config 2: one pair, N = 1e6 shared samples, per-sample decisions ---------------------------------
+@pytest.mark.parametrize("ndof", [3, 5])
+def test_cfg2_decisions_and_count_bit_exact(ctx, dev, oracle, workloads, ndof):
+    pair = workloads.cfg2_pair()
+    if ndof == 5:
+        pair["sd_w"] = 0.2; pair["sd_h"] = 0.1
+    n = 1_000_000
+    z = workloads.normal_bank(n, ndof, seed=2)
+    k_ref, dec_ref = oracle.count_streamed(pair, z, want_decisions=True)
+    d_z = dev.put(z.ravel()); d_pair = dev.put(pair)
+    for flags in (0, EXACT):
+        d_out = dev.zeros(n, np.uint8)
+        ctx.decide_streamed(d_pair, d_z, n, ndof, n, d_out, flags=flags)
+        np.testing.assert_array_equal(dev.get(d_out), dec_ref)
+        assert int(streamed(ctx, dev, pair, z, flags=flags)[0]) == k_ref
+    assert 0.05 < k_ref / n < 0.5
+
+
+def test_cfg2_matches_reference_device_functions(ctx, dev, refgpu, workloads):
+    """Same decisions as the reference binary: sample corners from its sample_rectangle, SAT by its convex_collide."""
+    pair = workloads.cfg2_pair(); pair["sd_w"] = 0.15; pair["sd_h"] = 0.05
+    n_per = 5000
+    rin = np.array([[-pair["ow"][0] / 2, -pair["oh"][0] / 2, pair["ow"][0] / 2, -pair["oh"][0] / 2,
+                     pair["ow"][0] / 2, pair["oh"][0] / 2, -pair["ow"][0] / 2, pair["oh"][0] / 2]], np.float32)
+    sd = np.array([[pair[k][0] for k in ("sd_x", "sd_y", "sd_theta", "sd_w", "sd_h")]], np.float32)
+    z, corners = refgpu.sample_record(rin, sd, n_per, seed=9)
+    robot = np.array([-pair["rw"][0] / 2, -pair["rh"][0] / 2, pair["rw"][0] / 2, -pair["rh"][0] / 2,
+                      pair["rw"][0] / 2, pair["rh"][0] / 2, -pair["rw"][0] / 2, pair["rh"][0] / 2], np.float32)
+    robot = refgpu.rot_trans(robot[None], pair["rx"], pair["ry"], pair["rtheta"])[0]
+    want = refgpu.convex_collide(np.tile(robot, (n_per, 1)), corners).astype(np.uint8)
+    d_out = dev.zeros(n_per, np.uint8)
+    ctx.decide_streamed(dev.put(pair), dev.put(z.ravel()), n_per, 5, n_per, d_out)
+    np.testing.assert_array_equal(dev.get(d_out), want)
+
+
+# ---- the reference's own kernel on the normals it drew ---------------------------------------------
+def test_streamed_counts_equal_reference_kernel(ctx, dev, refgpu, workloads):
+    pairs = workloads.dataset_pairs(1500, seed=41, shape_variance=True)
+    pairs["sd_w"][::3] = 0; pairs["sd_h"][::3] = 0
+    robot_base, poses, sds, pi, si, pos = workloads.reference_tables(pairs)
+    n_batch = 256
+    bins = np.array([0, 0.01, 0.1, 1.0], np.float32); acc = np.zeros(3, np.float32)
+    cps, _, z = refgpu.mc_run(robot_base, poses, sds, pi, si, pos, np.zeros(pairs.size, np.float32), bins, acc,
+                              n_batch, n_batch, seed=8)
+    got = streamed(ctx, dev, pairs, z, n=n_batch, z_pair_stride=n_batch)
+    np.testing.assert_array_equal(got.astype(np.int64), cps.astype(np.int64))
+
+
+# ---- many pairs, ragged sizes, both load paths ---------------------------------------------------
+@pytest.mark.parametrize("n", [1, 31, 33, 127, 129, 1000, 4097])
+@pytest.mark.parametrize("ndof", [3, 5])
+def test_streamed_ragged_sizes(ctx, dev, oracle, workloads, n, ndof):
+    pairs = workloads.dataset_pairs(37, seed=50 + n, shape_variance=(ndof == 5))
+    z = workloads.normal_bank(n, ndof, seed=n)
+    want = oracle.count_streamed_batch(pairs, z, n)
+    np.testing.assert_array_equal(streamed(ctx, dev, pairs, z), want)
+    np.testing.assert_array_equal(streamed(ctx, dev, pairs, z, misalign=True), want)
+    np.testing.assert_array_equal(streamed(ctx, dev, pairs, z, flags=EXACT), want)
+
+
+def test_streamed_cfg3_slice(ctx, dev, oracle, workloads):
+    pairs = workloads.dataset_pairs(3000, seed=3)
+    z = workloads.normal_bank(4096, 3, seed=33)
+    want = oracle.count_streamed_batch(pairs, z, 4096)
+    ctx.exact_evals(reset=True)
+    got = streamed(ctx, dev, pairs, z)
+    np.testing.assert_array_equal(got, want)
+    frac = ctx.exact_evals() / (3000 * 4096)
+    assert frac < 2e-3, f"screening pass falls back too often: {frac}"
+
+
+def test_streamed_private_slices_and_single_pair_many_chunks(ctx, dev, oracle, workloads):
+    pairs = workloads.dataset_pairs(5, seed=71)
+    n = 50_000
+    z = workloads.normal_bank(5 * n, 3, seed=72)
+    want = oracle.count_streamed_batch(pairs, z, n, z_pair_stride=n)
+    np.testing.assert_array_equal(streamed(ctx, dev, pairs, z, n=n, z_pair_stride=n), want)   # chunked + block reduction
+    one = pairs[:1]
+    assert int(streamed(ctx, dev, one, z)[0]) == oracle.count_streamed(one, z)
+
+
+def test_zero_samples_and_accumulate(ctx, dev, oracle, workloads):
+    pairs = workloads.dataset_pairs(9, seed=5)
+    z = workloads.normal_bank(640, 3, seed=6)
+    d_pairs, d_z = dev.put(pairs), dev.put(z.ravel())
+    d_hits = dev.put(np.full(9, 7, np.uint64))
+    ctx.count_streamed(d_pairs, 9, d_z, 640, 3, 0, d_hits)                     # n = 0 overwrites with zeros
+    ctx.synchronize()
+    np.testing.assert_array_equal(dev.get(d_hits, np.uint64), np.zeros(9, np.uint64))
+    want = oracle.count_streamed_batch(pairs, z, 640)
+    ctx.count_streamed(d_pairs, 9, d_z, 640, 3, 640, d_hits, flags=ACC)
+    ctx.count_streamed(d_pairs, 9, d_z, 640, 3, 640, d_hits, flags=ACC)
+    ctx.synchronize()
+    np.testing.assert_array_equal(dev.get(d_hits, np.uint64), 2 * want)
+
+
+# ---- hostile inputs: NaN / Inf / huge normals, degenerate rectangles, zero sigma ------------------------
+def test_nonfinite_and_huge_normals(ctx, dev, oracle, workloads):
+    pairs = workloads.dataset_pairs(16, seed=81, shape_variance=True)
+    z = workloads.normal_bank(512, 5, seed=82)
+    z[0, ::7] = np.nan; z[1, 3::11] = np.inf; z[2, 5::13] = -np.inf; z[3, ::17] = 1e30; z[2, 1::19] = 2e5
+    z[4, 2::23] = -50.0; z[0, 4::29] = 9.0
+    want = oracle.count_streamed_batch(pairs, z, 512)
+    np.testing.assert_array_equal(streamed(ctx, dev, pairs, z), want)
+    np.testing.assert_array_equal(streamed(ctx, dev, pairs, z[:3].copy()), oracle.count_streamed_batch(pairs, z[:3].copy(), 512))
+
+
+def test_degenerate_pairs(ctx, dev, oracle, satmc, workloads):
+    P = satmc.pairs_from_columns
+    pairs = np.concatenate([
+        P(1.0, 0.5, 0.3, 0.0, 1.0, 0.3, 0.3, 0.3),               # zero-width obstacle
+        P(1.0, 0.5, 0.3, 2.0, 1.0, 0.3, 0.3, 0.3, rw=0.0),       # zero-width robot
+        P(1.0, 0.5, 0.3, -2.0, 1.0, 0.3, 0.3, 0.3),              # negative width (flipped corners)
+        P(1.0, 0.5, 0.3, 2.0, 1.0, 0.0, 0.0, 0.0),               # all sigma zero
+        P(1e-3, 0.0, 0.0, 1e-3, 1e-3, 1e-4, 1e-4, 0.1, rw=1e-3, rh=1e-3),   # tiny everything
+        P(1e6, 1e6, 1.0, 2.0, 1.0, 0.3, 0.3, 0.3),               # far from the origin
+        P(np.nan, 0.5, 0.3, 2.0, 1.0, 0.3, 0.3, 0.3),            # NaN position
+        P(1.0, 0.5, 0.3, 2.0, 1.0, 0.3, 0.3, 30.0),              # huge angular sigma
+        P(1.0, 0.5, 0.3, 0.4, 0.3, 0.1, 0.1, 0.1, 1.0, 1.0),     # shape sigma larger than the shape
+        P(3.0, 0.0, 0.0, 2.0, 2.0, 0.0, 0.0, 0.0, rw=4.0, rh=2.0),   # exactly touching, sigma zero
+    ])
+    z = workloads.normal_bank(2048, 5, seed=90)
+    want = oracle.count_streamed_batch(pairs, z, 2048)
+    np.testing.assert_array_equal(streamed(ctx, dev, pairs, z), want)
+    assert want[9] == 2048                                         # touching counts as collision
+
+
+def test_adversarial_near_boundary(ctx, dev, oracle, satmc):
+    """Samples within ~1e-6 of the decision boundary on every axis class: screening must defer, never guess."""
+    rng = np.random.default_rng(17)
+    rows = []
+    for _ in range(200):
+        ow, oh = rng.uniform(0.1, 5, 2); th = rng.uniform(0, 2 * np.pi)
+        a = (4.07 + ow) / 2
+        if rng.random() < 0.5:                      # face-to-face contact along x, robot parallel
+            rows.append((a + rng.normal(0, 2e-6), rng.uniform(-0.3, 0.3), 0.0, ow, oh))
+        else:                                       # generic orientation, pushed to first contact numerically
+            lo, hi = 0.0, 20.0
+            ang = rng.uniform(0, 2 * np.pi)
+            for _ in range(60):
+                mid = (lo + hi) / 2
+                p = satmc.pairs_from_columns(mid * math.cos(ang), mid * math.sin(ang), th, ow, oh, 0, 0, 0)
+                hit = oracle.count_streamed(p, np.zeros((3, 1), np.float32))
+                lo, hi = (mid, hi) if hit else (lo, mid)
+            rows.append((lo * math.cos(ang), lo * math.sin(ang), th, ow, oh))
+    rows = np.array(rows)
+    pairs = satmc.pairs_from_columns(rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3], rows[:, 4], 3e-6, 3e-6, 2e-6)
+    z = rng.standard_normal((3, 4096)).astype(np.float32)
+    want = oracle.count_streamed_batch(pairs, z, 4096)
+    ctx.exact_evals(reset=True)
+    got = streamed(ctx, dev, pairs, z)
+    np.testing.assert_array_equal(got, want)
+    assert ctx.exact_evals() > 0.5 * pairs.size * 4096            # almost everything must have been deferred
+    assert np.any((want > 0) & (want < 4096))                     # and the cases really straddle the boundary
+
+
+# ---- sampler ------------------------------------------------------------------------------------------
+def test_philox_kat_on_device(ctx, dev):
+    from test_oracle import KAT
+    for ctr, key, out in KAT:
+        d_out = dev.zeros(4, np.uint32)
+        ctx.philox_blocks(dev.put(np.array(ctr, np.uint32)), 1, key[0], key[1], d_out)
+        np.testing.assert_array_equal(dev.get(d_out, np.uint32), np.array(out, np.uint32))
+
+
+def test_philox_matches_oracle_random(ctx, dev, oracle):
+    rng = np.random.default_rng(1)
+    ctr = rng.integers(0, 2 ** 32, (500, 4), dtype=np.uint64).astype(np.uint32)
+    d_out = dev.zeros(2000, np.uint32)
+    ctx.philox_blocks(dev.put(ctr.ravel()), 500, 0xdeadbeef, 0x12345678, d_out)
+    got = dev.get(d_out, np.uint32).reshape(500, 4)
+    want = np.stack([oracle.philox(c, (0xdeadbeef, 0x12345678)) for c in ctr])
+    np.testing.assert_array_equal(got, want)
+
+
+def fused_normals(ctx, dev, seed, pair_id, offset, n):
+    d_z = dev.zeros(5 * n, np.float32)
+    ctx.fused_normals(seed, pair_id, offset, n, d_z, n)
+    ctx.synchronize()
+    return dev.get(d_z).reshape(5, n)
+
+
+def test_fused_normals_distribution_and_oracle_agreement(ctx, dev, oracle):
+    n = 2_000_000
+    z = fused_normals(ctx, dev, 99, 3, 1 << 33, n).astype(np.float64)          # offset crosses 32 bits
+    assert np.all(np.isfinite(z)) and np.abs(z).max() < 6.8
+    assert np.all(np.abs(z.mean(1)) < 4.9 / math.sqrt(n))
+    assert np.all(np.abs((z ** 2).mean(1) - 1) < 4.9 * math.sqrt(2 / n))
+    assert np.all(np.abs((z ** 4).mean(1) - 3) < 4.9 * math.sqrt(96 / n))
+    cc = np.corrcoef(z)
+    assert np.all(np.abs(cc - np.eye(5)) < 4.9 / math.sqrt(n))
+    for k in range(5):                                                         # tail mass P(|z| > 3) = 2.6998e-3
+        p = 2.699796e-3
+        assert abs((np.abs(z[k]) > 3).sum() - n * p) < 4.9 * math.sqrt(n * p)
+    zo = np.stack([oracle.fused_normals(99, 3, (1 << 33) + i) for i in range(2000)], 1)
+    assert np.abs(z[:, :2000] - zo).max() < 2e-5                               # same formula, MUFU vs libm
+
+
+@pytest.mark.parametrize("five", [False, True])
+def test_fused_count_equals_streamed_on_its_own_normals(ctx, dev, oracle, workloads, five):
+    pairs = workloads.dataset_pairs(12, seed=61, shape_variance=five)
+    n, seed, off = 20_000, 4242, 123_456_789_012
+    got = fused(ctx, dev, pairs, n, seed, sample_offset=off, pair_id_offset=1000)
+    got_exact = fused(ctx, dev, pairs, n, seed, sample_offset=off, pair_id_offset=1000, flags=EXACT)
+    np.testing.assert_array_equal(got, got_exact)
+    for i in range(pairs.size):
+        z = fused_normals(ctx, dev, seed, 1000 + i, off, n)
+        if not five:
+            z = z[:3].copy()
+        assert int(got[i]) == oracle.count_streamed(pairs[i:i + 1], z), i
+        assert int(got[i]) == int(streamed(ctx, dev, pairs[i:i + 1], z)[0]), i
+
+
+def test_fused_sharding_invariance(ctx, dev, workloads):
+    pairs = workloads.dataset_pairs(300, seed=77)
+    n, seed = 30_000, 5
+    whole = fused(ctx, dev, pairs, n, seed)
+    # by sample range (cfg 4 style): 4 unequal ranges, accumulated
+    d_hits = dev.zeros(pairs.size, np.uint64)
+    cuts = [0, 7_001, 7_002, 19_999, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        fused(ctx, dev, pairs, b - a, seed, sample_offset=a, flags=ACC, d_hits=d_hits)
+    np.testing.assert_array_equal(dev.get(d_hits, np.uint64), whole)
+    # by pair range (cfg 3 style)
+    parts = [fused(ctx, dev, pairs[a:b], n, seed, pair_id_offset=a) for a, b in ((0, 1), (1, 130), (130, 300))]
+    np.testing.assert_array_equal(np.concatenate(parts), whole)
+    # single pair spread over the whole GPU (many chunks, block reduction) == that pair inside the batch
+    one = fused(ctx, dev, pairs[5:6], n, seed, pair_id_offset=5)
+    assert int(one[0]) == int(whole[5])
+
+
+def test_fused_closed_form_probability(ctx, dev, satmc):
+    """Axis-aligned pair, only sd_x != 0: p = Phi((a-x0)/s) - Phi((-a-x0)/s); bound 4.9 sigma (two-sided ~1e-6)."""
+    from math import erf, sqrt
+    Phi = lambda t: 0.5 * (1 + erf(t / sqrt(2)))
+    x0, wr, wo = np.array([3.4, 3.0, 4.5, 2.0]), 4.07, 2.3
+    s = np.array([0.8, 0.3, 0.5, 1.5])
+    pairs = satmc.pairs_from_columns(x0, 0.2, 0.0, wo, 1.1, s, 0.0, 0.0)
+    n = 50_000_000
+    k = fused(ctx, dev, pairs, n, 2024).astype(np.float64)
+    a = (wr + wo) / 2
+    for i in range(4):
+        p = Phi((a - x0[i]) / s[i]) - Phi((-a - x0[i]) / s[i])
+        assert abs(k[i] - n * p) < 4.9 * math.sqrt(n * p * (1 - p)) + 1, (i, k[i] / n, p)
+
+
+def test_fused_vs_reference_kernel_statistically(ctx, dev, refgpu, workloads):
+    """Native RNG vs the reference's cuRAND estimate: |k_new - k_ref| <= 4.9 sqrt(2 N p(1-p)) + 1 per pair."""
+    pairs = workloads.dataset_pairs(2000, seed=91, shape_variance=True)
+    robot_base, poses, sds, pi, si, pos = workloads.reference_tables(pairs)
+    n = 20_000
+    bins = np.array([0, 0.01, 0.1, 1.0], np.float32); acc = np.zeros(3, np.float32)
+    cps, _, _ = refgpu.mc_run(robot_base, poses, sds, pi, si, pos, np.zeros(pairs.size, np.float32), bins, acc, n, n,
+                              seed=123, record=False)
+    k = fused(ctx, dev, pairs, n, 777).astype(np.float64)
+    p = (k + cps) / (2 * n)
+    bound = 4.9 * np.sqrt(2 * n * p * (1 - p)) + 1
+    assert np.all(np.abs(k - cps) <= bound), np.abs(k - cps).max()
+    assert 0.02 < (cps > 0).mean()                                  # the workload has real hits
+
+
+# ---- reference-compatible step --------------------------------------------------------------------------
+def test_mc_step_matches_oracle_tail(ctx, dev, oracle, workloads):
+    pairs = workloads.dataset_pairs(700, seed=15)
+    robot_base, poses, sds, pi, si, pos = workloads.reference_tables(pairs)
+    bins = np.array([0, 0.01, 0.1, 1.0], np.float32); acc = np.array([1e-2, 2e-2, 5e-2], np.float32)
+    n_batch, seed = 1000, 31
+    d = {k: dev.put(v) for k, v in dict(rb=robot_base, poses=poses.ravel(), sds=sds.ravel(), pi=pi, si=si,
+                                        pos=pos.ravel(), bins=bins, acc=acc).items()}
+    d_cps = dev.zeros(pairs.size, np.float32)
+    d_done = dev.zeros(pairs.size, np.int32)
+    total = np.zeros(pairs.size, np.int64)
+    for it in range(3):
+        n_samples = (it + 1) * n_batch
+        ctx.mc_step(d["rb"], d["poses"], pairs.size, d["sds"], pairs.size, d["pi"], d["si"], d["pos"], d_cps,
+                    d["bins"], d["acc"], 4, d_done, it, n_samples, n_batch, pairs.size, seed, 0)
+        ctx.synchronize()
+        total += fused(ctx, dev, pairs, n_batch, seed, sample_offset=it * n_batch).astype(np.int64)
+        cps = dev.get(d_cps); done = dev.get(d_done)
+        np.testing.assert_array_equal(cps.astype(np.int64), total)
+        for g in range(0, pairs.size, 7):
+            slack = oracle.calc_slack(n_samples, int(total[g]))
+            want = int(slack <= acc[oracle.get_bin(np.float32(total[g]) / np.float32(n_samples), bins)])
+            assert done[g] == want, (it, g)
+    ctx.write_collision_probability(d_cps, pairs.size, 3 * n_batch)
+    ctx.synchronize()
+    np.testing.assert_array_equal(dev.get(d_cps), total.astype(np.float32) / np.float32(3 * n_batch))
+
+
+# ---- host-buffer entry points ---------------------------------------------------------------------------
+def test_host_entry_points(ctx, dev, oracle, workloads):
+    pairs = workloads.dataset_pairs(257, seed=19)
+    z = workloads.normal_bank(1001, 3, seed=20)
+    np.testing.assert_array_equal(ctx.count_streamed_host(pairs, z), oracle.count_streamed_batch(pairs, z, 1001))
+    h = ctx.count_fused_host(pairs, 5000, 11)
+    np.testing.assert_array_equal(h, fused(ctx, dev, pairs, 5000, 11))
+    cp = ctx.collision_probability_host(pairs, 5000, 11)
+    np.testing.assert_array_equal(cp, h.astype(np.float32) / np.float32(5000))
+    assert ctx.last_kernel_ms() > 0
+
+
+def test_argument_errors(ctx, dev, satmc, workloads):
+    pairs = workloads.dataset_pairs(4, seed=1)
+    z = workloads.normal_bank(64, 3, seed=1)
+    with pytest.raises(satmc.SatmcError):
+        ctx.count_streamed(dev.put(pairs), 4, dev.put(z.ravel()), 64, 4, 64, dev.zeros(4, np.uint64))      # ndof 4
+    with pytest.raises(satmc.SatmcError):
+        ctx.count_streamed(dev.put(pairs), 4, dev.put(z.ravel()), 64, 3, 65, dev.zeros(4, np.uint64))      # plane too short
+    with pytest.raises(satmc.SatmcError):
+        ctx.count_fused(0, 4, 10, 1, dev.zeros(4, np.uint64))                                              # null pairs
