@@ -24,6 +24,9 @@ namespace satmc {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
+#ifndef SATMC_MIN_BLOCKS
+#define SATMC_MIN_BLOCKS 2
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // pair sources
@@ -67,29 +70,40 @@ struct CountParams {
     uint64_t n_items;          // n_pairs * n_chunks
     uint32_t n_chunks;
     uint32_t pair_id_offset;
-    uint32_t k0, k1;
     uint32_t flags;            // SATMC_ACCUMULATE | SATMC_EXACT_ONLY
     uint32_t block_uniform;    // all warps of a block share a pair -> block reduction
     unsigned long long* hits;
     unsigned long long* exact_evals;
     // streamed
     const float* z; uint64_t ldz; uint64_t z_pair_stride; int ndof; int vec_ok;
+    PhiloxKeys keys;           // fused: round keys, read straight from the constant bank
 };
+
+// Cold path of the fused sampler: regenerate the normals of sample s (counter-based, so nothing
+// has to stay live across the hot loop) and decide with the exact reference arithmetic.
+template <int NDOF>
+__device__ __noinline__ unsigned fused_exact(const PairConst& P, const float* robot, uint64_t s, uint32_t pid,
+                                             const PhiloxKeys& K, unsigned long long* exact_evals)
+{
+    float z0, z1, z2, z3, z4 = 0.0f;
+    normals4<NDOF == 5>((uint32_t)s, (uint32_t)(s >> 32), pid, K, z0, z1, z2, z3);
+    if (NDOF == 5) z4 = normal5th((uint32_t)s, (uint32_t)(s >> 32), pid, K);
+    if (exact_evals) atomicAdd(exact_evals, 1ull);
+    return (unsigned)exact_decide(robot, P.ow, P.oh, P.sd_x, P.sd_y, P.sd_t, P.sd_w, P.sd_h, z0, z1, z2, z3, z4);
+}
 
 // one sample of the fused path
 template <int NDOF>
 __device__ __forceinline__ unsigned fused_sample(const PairConst& P, const float* robot, uint64_t s, uint32_t pid,
-                                                 uint32_t k0, uint32_t k1, unsigned long long* exact_evals)
+                                                 const PhiloxKeys& K, unsigned long long* exact_evals)
 {
-    float z0, z1, z2, z3, z4 = 0.0f;
-    normals4<NDOF == 5>((uint32_t)s, (uint32_t)(s >> 32), pid, k0, k1, z0, z1, z2, z3);
-    if (NDOF == 5) z4 = normal5th((uint32_t)s, (uint32_t)(s >> 32), pid, k0, k1);
-    const float m = screen_gap<NDOF>(P, z0, z1, z2, z3, z4);
-    unsigned hit = m < 0.0f;
-    if (!(fabsf(m) > P.eps)) {                                      // undecided (or NaN): exact arithmetic
-        hit = (unsigned)exact_decide(robot, P.ow, P.oh, P.sd_x, P.sd_y, P.sd_t, P.sd_w, P.sd_h, z0, z1, z2, z3, z4);
-        if (exact_evals) atomicAdd(exact_evals, 1ull);
-    }
+    float z0, z1, z2, z3, z4 = 0.0f, hmin;
+    normals4<NDOF == 5>((uint32_t)s, (uint32_t)(s >> 32), pid, K, z0, z1, z2, z3);
+    if (NDOF == 5) z4 = normal5th((uint32_t)s, (uint32_t)(s >> 32), pid, K);
+    const float m = screen_gap<NDOF>(P, z0, z1, z2, z3, z4, hmin);
+    unsigned hit = __float_as_uint(m) >> 31;                        // m < 0 (m = -0 / NaN are undecided anyway)
+    if (!screen_decided<NDOF>(P, m, hmin))                          // undecided (or NaN): exact arithmetic
+        hit = fused_exact<NDOF>(P, robot, s, pid, K, exact_evals);
     return hit;
 }
 
@@ -98,10 +112,11 @@ template <int NDOF>
 __device__ __forceinline__ unsigned streamed_sample(const PairConst& P, const float* robot, float z0, float z1,
                                                     float z2, float z3, float z4, unsigned long long* exact_evals)
 {
-    const float m = screen_gap<NDOF>(P, z0, z1, z2, z3, z4);
-    unsigned hit = m < 0.0f;
-    // the screening bound assumes |z| <= SATMC_Z_BOUND; ">" is false for NaN, so NaN/Inf go exact
-    bool ok = fabsf(m) > P.eps;
+    float hmin;
+    const float m = screen_gap<NDOF>(P, z0, z1, z2, z3, z4, hmin);
+    unsigned hit = __float_as_uint(m) >> 31;
+    // the screening bound assumes |z| <= SATMC_Z_BOUND; "<=" is false for NaN, so NaN/Inf go exact
+    bool ok = screen_decided<NDOF>(P, m, hmin);
     ok = ok && (fabsf(z0) <= SATMC_Z_BOUND) && (fabsf(z1) <= SATMC_Z_BOUND) && (fabsf(z2) <= SATMC_Z_BOUND);
     if (NDOF == 5) ok = ok && (fabsf(z3) <= SATMC_Z_BOUND) && (fabsf(z4) <= SATMC_Z_BOUND);
     if (!ok) {
@@ -113,17 +128,17 @@ __device__ __forceinline__ unsigned streamed_sample(const PairConst& P, const fl
 
 template <int NDOF>
 __device__ __forceinline__ unsigned fused_chunk(const PairConst& P, const float* robot, uint64_t s_begin, uint64_t len,
-                                                uint32_t pid, uint32_t k0, uint32_t k1, int lane,
+                                                uint32_t pid, const PhiloxKeys& K, int lane,
                                                 unsigned long long* exact_evals)
 {
     unsigned cnt = 0;
     uint64_t i = (uint64_t)lane;
     // two independent samples per trip: hides the serial Philox round chain
     for (; i + 32 < len; i += 64) {
-        cnt += fused_sample<NDOF>(P, robot, s_begin + i, pid, k0, k1, exact_evals);
-        cnt += fused_sample<NDOF>(P, robot, s_begin + i + 32, pid, k0, k1, exact_evals);
+        cnt += fused_sample<NDOF>(P, robot, s_begin + i, pid, K, exact_evals);
+        cnt += fused_sample<NDOF>(P, robot, s_begin + i + 32, pid, K, exact_evals);
     }
-    if (i < len) cnt += fused_sample<NDOF>(P, robot, s_begin + i, pid, k0, k1, exact_evals);
+    if (i < len) cnt += fused_sample<NDOF>(P, robot, s_begin + i, pid, K, exact_evals);
     return cnt;
 }
 
@@ -162,7 +177,7 @@ __device__ __forceinline__ unsigned streamed_chunk(const PairConst& P, const flo
 }
 
 template <class Src, bool STREAMED>
-__global__ void __launch_bounds__(kThreads) k_count(Src src, CountParams p)
+__global__ void __launch_bounds__(kThreads, SATMC_MIN_BLOCKS) k_count(const __grid_constant__ Src src, const __grid_constant__ CountParams p)
 {
     __shared__ float s_robot[kWarps][8];
     __shared__ unsigned s_part[kWarps];
@@ -176,7 +191,7 @@ __global__ void __launch_bounds__(kThreads) k_count(Src src, CountParams p)
         src.load(pair, v);
         PairConst P;
         pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
-        if (p.flags & SATMC_EXACT_ONLY) P.eps = CUDART_INF_F;
+        if (p.flags & SATMC_EXACT_ONLY) { P.eps = CUDART_INF_F; P.eps_b = CUDART_INF_F; }
         __syncwarp();
         if (lane == 0) exact_robot_corners(v[0], v[1], v[2], v[3], v[4], s_robot[warp]);
         __syncwarp();
@@ -192,8 +207,8 @@ __global__ void __launch_bounds__(kThreads) k_count(Src src, CountParams p)
             const uint32_t pid = p.pair_id_offset + (uint32_t)pair;
             const uint64_t s_begin = p.sample_offset + c_begin;
             const bool dof3 = (v[10] == 0.0f) && (v[11] == 0.0f);
-            cnt = dof3 ? fused_chunk<3>(P, s_robot[warp], s_begin, c_len, pid, p.k0, p.k1, lane, ev)
-                       : fused_chunk<5>(P, s_robot[warp], s_begin, c_len, pid, p.k0, p.k1, lane, ev);
+            cnt = dof3 ? fused_chunk<3>(P, s_robot[warp], s_begin, c_len, pid, p.keys, lane, ev)
+                       : fused_chunk<5>(P, s_robot[warp], s_begin, c_len, pid, p.keys, lane, ev);
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (p.block_uniform) {
@@ -228,7 +243,7 @@ __global__ void k_decide(satmc_pair const* pair, const float* __restrict__ z, ui
     src.load(0, v);
     PairConst P;
     pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
-    if (flags & SATMC_EXACT_ONLY) P.eps = CUDART_INF_F;
+    if (flags & SATMC_EXACT_ONLY) { P.eps = CUDART_INF_F; P.eps_b = CUDART_INF_F; }
     if (threadIdx.x == 0) exact_robot_corners(v[0], v[1], v[2], v[3], v[4], s_robot);
     __syncthreads();
     unsigned long long* ev = (flags & SATMC_EXACT_ONLY) ? nullptr : exact_evals;
@@ -241,23 +256,23 @@ __global__ void k_decide(satmc_pair const* pair, const float* __restrict__ z, ui
     }
 }
 
-__global__ void k_fused_normals(uint32_t k0, uint32_t k1, uint32_t pid, uint64_t offset, uint64_t n, float* z, uint64_t ldz)
+__global__ void k_fused_normals(const __grid_constant__ PhiloxKeys K, uint32_t pid, uint64_t offset, uint64_t n, float* z, uint64_t ldz)
 {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t s = offset + i;
         float z0, z1, z2, z3;
-        normals4<true>((uint32_t)s, (uint32_t)(s >> 32), pid, k0, k1, z0, z1, z2, z3);
-        const float z4 = normal5th((uint32_t)s, (uint32_t)(s >> 32), pid, k0, k1);
+        normals4<true>((uint32_t)s, (uint32_t)(s >> 32), pid, K, z0, z1, z2, z3);
+        const float z4 = normal5th((uint32_t)s, (uint32_t)(s >> 32), pid, K);
         z[i] = z0; z[ldz + i] = z1; z[2 * ldz + i] = z2; z[3 * ldz + i] = z3; z[4 * ldz + i] = z4;
     }
 }
 
-__global__ void k_philox(const uint32_t* ctr, uint64_t n, uint32_t k0, uint32_t k1, uint32_t* out)
+__global__ void k_philox(const uint32_t* ctr, uint64_t n, const __grid_constant__ PhiloxKeys K, uint32_t* out)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t w[4];
-    philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], k0, k1, w);
+    philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], K, w);
     out[4 * i] = w[0]; out[4 * i + 1] = w[1]; out[4 * i + 2] = w[2]; out[4 * i + 3] = w[3];
 }
 
@@ -538,7 +553,7 @@ int satmc_count_fused(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pair
     DeviceGuard g(ctx->device);
     CountParams p{};
     p.n_pairs = n_pairs; p.n_samples = n_samples; p.sample_offset = sample_offset; p.pair_id_offset = pair_id_offset;
-    p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32); p.flags = flags;
+    philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), p.keys); p.flags = flags;
     p.hits = reinterpret_cast<unsigned long long*>(d_hits); p.exact_evals = ctx->d_exact_evals;
     return launch_count<DirectSrc, false>(ctx, DirectSrc{d_pairs}, p, ctx->profiling);
 }
@@ -582,8 +597,8 @@ int satmc_fused_normals(satmc_ctx* ctx, uint64_t seed, uint32_t pair_id, uint64_
     DeviceGuard g(ctx->device);
     uint64_t blocks = (n + 255) / 256;
     if (blocks > (uint64_t)ctx->sm_count * 8) blocks = (uint64_t)ctx->sm_count * 8;
-    k_fused_normals<<<(unsigned)blocks, 256, 0, ctx->stream>>>((uint32_t)seed, (uint32_t)(seed >> 32), pair_id, sample_offset, n,
-                                                              d_z, ldz);
+    PhiloxKeys K; philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), K);
+    k_fused_normals<<<(unsigned)blocks, 256, 0, ctx->stream>>>(K, pair_id, sample_offset, n, d_z, ldz);
     CU(ctx, cudaGetLastError());
     ctx->launches++;
     return SATMC_OK;
@@ -595,7 +610,8 @@ int satmc_philox_blocks(satmc_ctx* ctx, const uint32_t* d_ctr, uint64_t n, uint3
     if (!d_ctr || !d_out) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
     if (n == 0) return SATMC_OK;
     DeviceGuard g(ctx->device);
-    k_philox<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_ctr, n, key0, key1, d_out);
+    PhiloxKeys K; philox_expand_key(key0, key1, K);
+    k_philox<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_ctr, n, K, d_out);
     CU(ctx, cudaGetLastError());
     ctx->launches++;
     return SATMC_OK;
@@ -635,7 +651,7 @@ int satmc_mc_step(satmc_ctx* ctx, const float* d_robot_base, const float* d_pose
     if (rc) return rc;
     CountParams p{};
     p.n_pairs = (uint64_t)num_left; p.n_samples = (uint64_t)n_batch; p.sample_offset = (uint64_t)(n_samples - n_batch);
-    p.pair_id_offset = stream_id_offset; p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32); p.flags = 0;
+    p.pair_id_offset = stream_id_offset; philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), p.keys); p.flags = 0;
     p.hits = reinterpret_cast<unsigned long long*>(d_hits); p.exact_evals = ctx->d_exact_evals;
     IndirectSrc src{d_robot_base, d_poses, d_std_devs, d_pose_idxs, d_std_dev_idxs, d_positions, n_poses, n_std};
     if (n_batch == 0) CU(ctx, cudaMemsetAsync(d_hits, 0, (size_t)num_left * sizeof(unsigned long long), ctx->stream));

@@ -117,41 +117,46 @@ struct PairConst {
     float ca, sa;
     float a0, a1, b0, b1;
     float hw, hh;                    // 0.5*sd_w, 0.5*sd_h  (5-DoF half-extent perturbation)
-    float eps;                       // screening threshold; +inf => always exact
+    float eps;                       // 3-DoF screening threshold eps_a + eps_b / min(b0,b1); +inf => always exact
+    float eps_a, eps_b;              // 5-DoF: decided iff hmin > 0 and (|m| - eps_a) * hmin > eps_b, hmin = min(hx, hy)
     // exact pass
     float ow, oh, sd_x, sd_y, sd_t, sd_w, sd_h;
 };
 
-// Screening threshold eps.  u = 2^-24.  All quantities are upper bounds over
-// every sample with |z_k| <= SATMC_Z_BOUND:
+// Screening threshold.  u = 2^-24.  All quantities are upper bounds over every
+// sample with |z_k| <= SATMC_Z_BOUND:
 //   E_ref  : |exact-arithmetic normalised gap of the reference's rounded quads on its rounded edge
 //             axis  -  gap of the ideal rectangles on the ideal axis|
 //   E_fast : |screening value  -  gap of the ideal rectangles|
-__device__ __forceinline__ float screen_eps(float px, float py, float a0, float a1, float b0, float b1,
-                                            float sd_x, float sd_y, float sd_t, float sd_w, float sd_h)
+// The bound has the form eps = eps_a + eps_b / hmin, hmin = the smaller obstacle half extent (the
+// obstacle's edge axes are known to relative accuracy ~ corner error / edge length).  With shape
+// variance hmin changes per sample, so the two parts are kept separate.
+__device__ __forceinline__ void screen_eps(float px, float py, float a0, float a1, float b0, float b1,
+                                           float sd_x, float sd_y, float sd_t, float sd_w, float sd_h,
+                                           float& eps_a, float& eps_b)
 {
     const float u = 5.9604645e-8f;
     const float Z = SATMC_Z_BOUND;
     const float dmx = Z * fabsf(sd_x), dmy = Z * fabsf(sd_y), dmt = Z * fabsf(sd_t);
     const float dmw = 0.5f * Z * fabsf(sd_w), dmh = 0.5f * Z * fabsf(sd_h);
-    const float hx_max = b0 + dmw, hy_max = b1 + dmh;
-    const float hx_min = b0 - dmw, hy_min = b1 - dmh;
+    const float hx_max = fabsf(b0) + dmw, hy_max = fabsf(b1) + dmh;
     const float r1a = a0 + a1, r1b = hx_max + hy_max;
     const float pn = fabsf(px) + fabsf(py), dn = dmx + dmy;
     const float un = pn + dn;
     const float M = un + r1a + r1b;
     const float dS = u * (7.0f * r1b + fmaxf(dmx, dmy));
     const float dR = u * (7.0f * r1a + pn);
-    const float LB = 2.0f * fminf(hx_min, hy_min);
     const float LA = 2.0f * fminf(a0, a1);
-    const float e_ref = 5.5f * u * M + 1.5f * (dS + dR) + 3.0f * M * fmaxf(dS / LB, dR / LA);
     const float e_m = 9.5367432e-7f + 4.0f * u * dmt;                 // |__sinf/__cosf - sin/cos|, |x| <= dmt
     const float e_fast = (un + 2.0f * (r1a + r1b)) * e_m + 24.0f * u * M;
-    float eps = 1.0625f * (e_ref + e_fast);
-    // outside the validated domain of the bound: degenerate or flipped rectangles, huge angles,
-    // non-finite input -> never trust the screening pass
-    const bool ok = (LB > 0.0f) && (LA > 0.0f) && (dmt <= 64.0f) && (eps == eps) && (M < 1.0e18f);
-    return ok ? eps : CUDART_INF_F;
+    const float e_ref_a = 5.5f * u * M + 1.5f * (dS + dR) + 3.0f * M * dR / LA;
+    float ea = 1.0625f * (e_ref_a + e_fast);
+    float eb = 1.0625f * 1.5f * M * dS;                               // 3 M dS / LB, LB = 2 hmin
+    // outside the validated domain of the bound (degenerate robot, huge angles, non-finite or
+    // astronomically large input): never trust the screening pass
+    const bool ok = (LA > 0.0f) && (dmt <= 64.0f) && (ea == ea) && (eb == eb) && (M < 1.0e18f);
+    eps_a = ok ? ea : CUDART_INF_F;
+    eps_b = ok ? eb : CUDART_INF_F;
 }
 
 __device__ __forceinline__ void pair_const_init(PairConst& P, float rx, float ry, float rtheta, float rw,
@@ -169,14 +174,18 @@ __device__ __forceinline__ void pair_const_init(PairConst& P, float rx, float ry
     P.b0 = 0.5f * ow;        P.b1 = 0.5f * oh;
     P.hw = 0.5f * sd_w;      P.hh = 0.5f * sd_h;
     P.ow = ow; P.oh = oh; P.sd_x = sd_x; P.sd_y = sd_y; P.sd_t = sd_t; P.sd_w = sd_w; P.sd_h = sd_h;
-    P.eps = screen_eps(rx, ry, P.a0, P.a1, P.b0, P.b1, sd_x, sd_y, sd_t, sd_w, sd_h);
+    screen_eps(rx, ry, P.a0, P.a1, P.b0, P.b1, sd_x, sd_y, sd_t, sd_w, sd_h, P.eps_a, P.eps_b);
+    const float hmin = fminf(P.b0, P.b1);
+    const float e3 = P.eps_a + P.eps_b / hmin;
+    P.eps = (hmin > 0.0f && e3 == e3) ? e3 : CUDART_INF_F;
 }
 
 // ---------------------------------------------------------------------------------------------
 // screening pass: largest normalised signed gap over the 4 box axes (m > 0 separated, m < 0 overlap)
 // ---------------------------------------------------------------------------------------------
 template <int NDOF>
-__device__ __forceinline__ float screen_gap(const PairConst& P, float z0, float z1, float z2, float z3, float z4)
+__device__ __forceinline__ float screen_gap(const PairConst& P, float z0, float z1, float z2, float z3, float z4,
+                                            float& hmin)
 {
     const float dt = __fmul_rn(z2, P.sd_t);              // the same float the exact pass feeds to sinf/cosf
     const float s = __sinf(dt), c = __cosf(dt);
@@ -190,11 +199,20 @@ __device__ __forceinline__ float screen_gap(const PairConst& P, float z0, float 
     const float S = fabsf(fmaf(P.sa, c, -(P.ca * s)));
     float hx = P.b0, hy = P.b1;
     if (NDOF == 5) { hx = fmaf(z3, P.hw, hx); hy = fmaf(z4, P.hh, hy); }
+    hmin = fminf(hx, hy);
     const float tb0 = fabsf(ub0) - fmaf(P.a0, C, fmaf(P.a1, S, hx));
     const float tb1 = fabsf(ub1) - fmaf(P.a0, S, fmaf(P.a1, C, hy));
     const float ta0 = fabsf(ua0) - fmaf(hx, C, fmaf(hy, S, P.a0));
     const float ta1 = fabsf(ua1) - fmaf(hx, S, fmaf(hy, C, P.a1));
     return fmaxf(fmaxf(tb0, tb1), fmaxf(ta0, ta1));
+}
+
+// true iff the sign of m is provably the exact decision (false for NaN anywhere)
+template <int NDOF>
+__device__ __forceinline__ bool screen_decided(const PairConst& P, float m, float hmin)
+{
+    if (NDOF == 5) return (hmin > 0.0f) && ((fabsf(m) - P.eps_a) * hmin > P.eps_b);
+    return fabsf(m) > P.eps;
 }
 
 // Exact decision for one sample given the robot corners (kept in shared memory by the caller).

@@ -9,9 +9,10 @@
 //     j = 0 -> four 32-bit words -> two Box-Muller pairs -> z0 (x), z1 (y), z2 (theta), z3 (w)
 //     j = 1 -> one more pair                            -> z4 (h)          (5-DoF pairs only)
 //   Box-Muller on words (a, b):
-//     U     = RN(a + 0.5)                       (float, exact small values: 32-bit tail resolution,
-//                                                 largest radius sqrt(2*33*ln2) = 6.76 like cuRAND's 6.66)
-//     R     = sqrt(-2 ln(U * 2^-32))  =  sqrt(fma(log2 U, -2 ln2, 64 ln2))
+//     U     = RN((a + 0.5) * 2^-32)             (float in [2^-33, 1]; exact for small values, so the tail
+//                                                 has 32-bit resolution: largest radius sqrt(2*33*ln2) = 6.76,
+//                                                 cuRAND's is 6.66)
+//     R     = sqrt(-2 ln U) = sqrt(-2 ln2 * log2 U)
 //     phi   = 2 pi * ((b & 0x7fffff) + 0.5) * 2^-23
 //     (R cos phi, R sin phi)
 // log2/sqrt/sin/cos are the MUFU approximations: the normals are "native RNG" values, specified
@@ -28,17 +29,27 @@ namespace satmc {
 #define SATMC_PHILOX_W0 0x9E3779B9u
 #define SATMC_PHILOX_W1 0xBB67AE85u
 
-struct PhiloxKey { uint32_t k0, k1; };
+// The ten round keys (k0 + r*W0, k1 + r*W1) are precomputed on the host and live in the kernel
+// parameter (constant) bank, so a round is 2 IMAD.WIDE + 2 LOP3 with a constant operand.
+struct PhiloxKeys { uint32_t rk[20]; };
+
+__host__ __device__ inline void philox_expand_key(uint32_t k0, uint32_t k1, PhiloxKeys& K)
+{
+    for (int r = 0; r < 10; r++) {
+        K.rk[2 * r] = k0 + (uint32_t)r * SATMC_PHILOX_W0;
+        K.rk[2 * r + 1] = k1 + (uint32_t)r * SATMC_PHILOX_W1;
+    }
+}
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                              uint32_t k0, uint32_t k1, uint32_t out[4])
+                                              const PhiloxKeys& K, uint32_t out[4])
 {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
         const uint64_t p0 = (uint64_t)SATMC_PHILOX_M0 * c0;      // IMAD.WIDE.U32
         const uint64_t p1 = (uint64_t)SATMC_PHILOX_M1 * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ (k0 + (uint32_t)r * SATMC_PHILOX_W0);   // LOP3
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ (k1 + (uint32_t)r * SATMC_PHILOX_W1);
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.rk[2 * r];         // LOP3 with constant operand
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.rk[2 * r + 1];
         c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
@@ -49,16 +60,18 @@ __device__ __forceinline__ float mufu_sqrt(float x) { float y; asm("sqrt.approx.
 __device__ __forceinline__ float mufu_sin(float x)  { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_cos(float x)  { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// radius of the Box-Muller pair from one 32-bit word
+// radius of the Box-Muller pair from one 32-bit word:  U = (a + 0.5) * 2^-32 in (0,1], R = sqrt(-2 ln U)
 __device__ __forceinline__ float bm_radius(uint32_t a)
 {
-    // (float)(a >> 16) and (float)(a & 0xffff) through the 2^23 magic exponent: two PRMTs, no I2F
-    const float hf = __uint_as_float(__byte_perm(a, 0x4b000000u, 0x7632));   // 2^23 + (a >> 16)
-    const float lf = __uint_as_float(__byte_perm(a, 0x4b000000u, 0x7610));   // 2^23 + (a & 0xffff)
-    const float hi = __fmaf_rn(hf, 65536.0f, -549755813888.0f);              // (a >> 16) * 2^16, exact
-    const float lo = __fadd_rn(lf, -8388607.5f);                             // (a & 0xffff) + 0.5, exact
-    const float U = __fadd_rn(hi, lo);                                       // RN(a + 0.5) in [0.5, 2^32]
-    const float r2 = __fmaf_rn(mufu_lg2(U), -1.3862943611198906f, 44.361419555836500f);
+    // (a >> 16) * 2^-16 and (a & 0xffff) * 2^-32 through magic exponents: two PRMTs, no I2F.
+    // U is formed near 1 for small radii, where lg2.approx is accurate to 2^-22 absolute, so the radius
+    // keeps ~1e-7 resolution at R -> 0 (the same resolution as cuRAND's float uniform + logf).
+    const float hf = __uint_as_float(__byte_perm(a, 0x43000000u, 0x7632));   // 128 + (a >> 16) * 2^-16
+    const float lf = __uint_as_float(__byte_perm(a, 0x3b000000u, 0x7610));   // 2^-9 + (a & 0xffff) * 2^-32
+    const float hi = __fadd_rn(hf, -128.0f);                                 // exact
+    const float lo = __fadd_rn(lf, -0.001953124883584678173065185546875f);   // - (2^-9 - 2^-33): (a & 0xffff + 0.5) * 2^-32, exact
+    const float U = __fadd_rn(hi, lo);                                       // RN((a + 0.5) * 2^-32) in [2^-33, 1]
+    const float r2 = __fmul_rn(mufu_lg2(U), -1.3862943611198906f);           // -2 ln U >= 0
     return mufu_sqrt(fabsf(r2));
 }
 
@@ -70,24 +83,24 @@ __device__ __forceinline__ float bm_angle(uint32_t b)
 
 // z0..z3 of sample (s, stream p); z3 only if WANT4
 template <bool WANT4>
-__device__ __forceinline__ void normals4(uint32_t s_lo, uint32_t s_hi, uint32_t p, uint32_t k0, uint32_t k1,
+__device__ __forceinline__ void normals4(uint32_t s_lo, uint32_t s_hi, uint32_t p, const PhiloxKeys& K,
                                          float& z0, float& z1, float& z2, float& z3)
 {
     uint32_t w[4];
-    philox4x32_10(s_lo, s_hi, p, 0u, k0, k1, w);
+    philox4x32_10(s_lo, s_hi, p, 0u, K, w);
     const float ra = bm_radius(w[0]), pa = bm_angle(w[1]);
     const float rb = bm_radius(w[2]), pb = bm_angle(w[3]);
-    z0 = ra * mufu_cos(pa);
-    z1 = ra * mufu_sin(pa);
-    z2 = rb * mufu_cos(pb);
-    z3 = WANT4 ? rb * mufu_sin(pb) : 0.0f;
+    z0 = __fmul_rn(ra, mufu_cos(pa));
+    z1 = __fmul_rn(ra, mufu_sin(pa));
+    z2 = __fmul_rn(rb, mufu_cos(pb));
+    z3 = WANT4 ? __fmul_rn(rb, mufu_sin(pb)) : 0.0f;
 }
 
-__device__ __forceinline__ float normal5th(uint32_t s_lo, uint32_t s_hi, uint32_t p, uint32_t k0, uint32_t k1)
+__device__ __forceinline__ float normal5th(uint32_t s_lo, uint32_t s_hi, uint32_t p, const PhiloxKeys& K)
 {
     uint32_t w[4];
-    philox4x32_10(s_lo, s_hi, p, 1u, k0, k1, w);
-    return bm_radius(w[0]) * mufu_cos(bm_angle(w[1]));
+    philox4x32_10(s_lo, s_hi, p, 1u, K, w);
+    return __fmul_rn(bm_radius(w[0]), mufu_cos(bm_angle(w[1])));
 }
 
 }  // namespace satmc

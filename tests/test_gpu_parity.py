@@ -256,7 +256,7 @@ def test_fused_normals_distribution_and_oracle_agreement(ctx, dev, oracle):
         p = 2.699796e-3
         assert abs((np.abs(z[k]) > 3).sum() - n * p) < 4.9 * math.sqrt(n * p)
     zo = np.stack([oracle.fused_normals(99, 3, (1 << 33) + i) for i in range(2000)], 1)
-    assert np.abs(z[:, :2000] - zo).max() < 2e-5                               # same formula, MUFU vs libm
+    assert np.abs(z[:, :2000] - zo).max() < 4e-6                               # same formula, MUFU vs libm
 
 
 @pytest.mark.parametrize("five", [False, True])

@@ -71,11 +71,12 @@ def main(out_dir):
     robot_base, poses, sds, pi, si, pos = wl.reference_tables(pairs)
     n_batch, n_samples = 200, 1200
     cps_in = rng.integers(0, 1000, pairs.size).astype(np.float32)
-    bins = np.array([0, 0.01, 0.1, 1.0], np.float32); acc = np.array([1e-2, 2e-2, 5e-2], np.float32)
+    bins = np.array([0, 0.01, 0.1, 1.0], np.float32); acc = np.array([2e-3, 1e-2, 2.2e-2], np.float32)
     cps_out, done, zrec = ref.mc_run(robot_base, poses, sds, pi, si, pos, cps_in, bins, acc, n_samples, n_batch, seed=5)
     np.savez_compressed(os.path.join(out_dir, "ref_mc_kernel.npz"), robot_base=robot_base, poses=poses, std_devs=sds,
                         pose_idxs=pi, sd_idxs=si, positions=pos, cps_in=cps_in, cps_out=cps_out, done=done, z=zrec,
                         n_batch=n_batch, n_samples=n_samples, bins=bins, bin_acc=acc)
+    print('mc kernel done flags set:', int(done.sum()), 'of', done.size)
     for f in sorted(os.listdir(out_dir)):
         print(f, os.path.getsize(os.path.join(out_dir, f)))
 

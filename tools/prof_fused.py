@@ -1,0 +1,25 @@
+#!/usr/bin/env python
+"""Short driver for ncu: a few launches of one counting kernel.  usage: prof_fused.py [fused|fused5|streamed3|streamed5|ztest]"""
+import importlib, os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+satmc = importlib.import_module("convex-2d-gpu-collision-detection_b200")
+wl = importlib.import_module("convex-2d-gpu-collision-detection_b200.workloads")
+mode = sys.argv[1] if len(sys.argv) > 1 else "fused"
+ctx = satmc.Context(0, torch.cuda.current_stream().cuda_stream)
+put = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.float32)).cuda()
+if mode in ("fused", "fused5", "ztest"):
+    pairs = wl.dataset_pairs(100_000, 3, shape_variance=(mode == "fused5"))
+    n = 1000 if mode == "ztest" else 10_000
+    d_pairs = put(pairs); d_hits = torch.zeros(pairs.size, dtype=torch.int64, device="cuda")
+    for _ in range(4):
+        ctx.count_fused(d_pairs, pairs.size, n, 7, d_hits)
+else:
+    ndof = 3 if mode == "streamed3" else 5
+    npairs, n = 16384, 32768
+    z = torch.randn(ndof * npairs * n, device="cuda")
+    pairs = wl.dataset_pairs(npairs, 9); d_pairs = put(pairs); d_hits = torch.zeros(npairs, dtype=torch.int64, device="cuda")
+    for _ in range(4):
+        ctx.count_streamed(d_pairs, npairs, z, npairs * n, ndof, n, d_hits, z_pair_stride=n)
+torch.cuda.synchronize()
+print(mode, "hits", int(d_hits.sum().item()), "launches", ctx.launch_count)

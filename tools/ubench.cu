@@ -1,0 +1,65 @@
+// tools/ubench.cu -- development probe: issue throughput (warp-instructions / clk / SM) of the
+// instruction classes the fused kernel is made of, measured with clock64 on one resident block per SM.
+// Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/ubench tools/ubench.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define ITERS 2048
+#define ILP 8
+
+template <int OP>
+__global__ void __launch_bounds__(1024, 1) k(uint32_t seed, uint32_t* sink, long long* cyc)
+{
+    uint32_t a[ILP]; float f[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; i++) { a[i] = seed + threadIdx.x * 977u + i * 131u; f[i] = 1.0f + (float)(a[i] & 1023) * 1e-3f; }
+    __syncthreads();
+    long long t0 = clock64();
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < ILP; i++) {
+            if (OP == 0) { uint64_t p = (uint64_t)a[i] * 0xD2511F53u; a[i] = (uint32_t)p ^ (uint32_t)(p >> 32); }          // IMAD.WIDE + LOP3
+            if (OP == 1) { a[i] = a[i] * 0xD2511F53u + seed; }                                                              // IMAD
+            if (OP == 2) { a[i] = (a[i] ^ seed) & (a[(i + 1) % ILP] | 0x55u); }                                             // LOP3
+            if (OP == 3) { f[i] = fmaf(f[i], 1.0000001f, 1e-9f); }                                                          // FFMA
+            if (OP == 4) { asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(f[i])); }                                       // MUFU
+            if (OP == 5) { a[i] = __byte_perm(a[i], seed, 0x7610 ^ (i & 1)); }                                              // PRMT
+            if (OP == 6) { f[i] = fmaxf(f[i], f[(i + 1) % ILP] * 0.5f); }                                                    // FMNMX + FMUL
+            if (OP == 7) { uint64_t p = (uint64_t)a[i] * 0xD2511F53u; a[i] = (uint32_t)(p >> 32) + (uint32_t)p; }            // IMAD.WIDE + IADD
+            if (OP == 8) { asm volatile("sin.approx.ftz.f32 %0, %0;" : "+f"(f[i])); }                                       // FMUL + MUFU.SIN
+            if (OP == 9) { f[i] = fmaf(f[i], 1.0000001f, 1e-9f); a[i] = a[i] * 0xD2511F53u + seed; }                         // FFMA + IMAD mix
+            if (OP == 10) { f[i] = fmaf(f[i], 1.0000001f, 1e-9f); a[i] = (a[i] ^ seed) & (a[(i + 1) % ILP] | 0x55u); }       // FFMA + LOP3 mix
+            if (OP == 11) { f[i] = f[i] + 1e-9f; }                                                                          // FADD
+        }
+    }
+    long long t1 = clock64();
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; i++) s += a[i] + __float_as_uint(f[i]);
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int OP> void run(const char* name, int instr_per_op)
+{
+    int sms = 148;
+    uint32_t* sink; long long* cyc;
+    cudaMalloc(&sink, sms * 1024 * 4); cudaMalloc(&cyc, sms * 8);
+    k<OP><<<sms, 1024>>>(12345u, sink, cyc);
+    k<OP><<<sms, 1024>>>(12345u, sink, cyc);
+    cudaDeviceSynchronize();
+    long long h[148]; cudaMemcpy(h, cyc, sms * 8, cudaMemcpyDeviceToHost);
+    double avg = 0; for (int i = 0; i < sms; i++) avg += h[i]; avg /= sms;
+    double warp_ops = 32.0 * ITERS * ILP;            // per SM: 32 warps
+    printf("%-28s %8.1f cyc  %6.3f ops/clk/SM (=%5.2f per SMSP)  ~%.3f warp-instr/clk/SM\n", name, avg, warp_ops / avg, warp_ops / avg / 4,
+           warp_ops * instr_per_op / avg);
+    cudaFree(sink); cudaFree(cyc);
+}
+
+int main()
+{
+    run<3>("FFMA", 1); run<11>("FADD", 1); run<1>("IMAD", 1); run<0>("IMAD.WIDE+LOP3", 2); run<7>("IMAD.WIDE+IADD3", 2); run<2>("LOP3(x2)", 2);
+    run<5>("PRMT", 1); run<6>("FMNMX+FMUL", 2); run<4>("MUFU.LG2", 1); run<8>("FMUL+MUFU.SIN", 2); run<9>("FFMA+IMAD", 2); run<10>("FFMA+LOP3x2", 3);
+    return 0;
+}
