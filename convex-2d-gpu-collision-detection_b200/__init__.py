@@ -39,7 +39,8 @@ ABI_SYMBOLS = (
     "satmc_launch_count", "satmc_set_profiling", "satmc_last_kernel_ms",
     "satmc_count_fused", "satmc_count_streamed", "satmc_decide_streamed", "satmc_fused_normals",
     "satmc_philox_blocks", "satmc_sat_corners", "satmc_exact_evals",
-    "satmc_mc_step", "satmc_write_collision_probability",
+    "satmc_mc_step", "satmc_write_collision_probability", "satmc_adaptive_run", "satmc_sample_positions",
+    "satmc_device_alloc", "satmc_device_free", "satmc_upload", "satmc_download",
     "satmc_count_fused_host", "satmc_count_streamed_host", "satmc_collision_probability_host",
     "satmc_host_alloc", "satmc_host_free",
 )
@@ -77,13 +78,20 @@ def load_library() -> ctypes.CDLL:
         "satmc_count_fused": (i32, [vp, vp, u64, u64, u64, u64, u32, vp, u32]),
         "satmc_count_streamed": (i32, [vp, vp, u64, f32p, u64, u64, i32, u64, vp, u32]),
         "satmc_decide_streamed": (i32, [vp, vp, f32p, u64, i32, u64, vp, u32]),
-        "satmc_fused_normals": (i32, [vp, u64, u32, u64, u64, f32p, u64]),
+        "satmc_fused_normals": (i32, [vp, u64, u32, u64, u64, i32, f32p, u64]),
         "satmc_philox_blocks": (i32, [vp, vp, u64, u32, u32, vp]),
         "satmc_sat_corners": (i32, [vp, f32p, f32p, u64, vp]),
         "satmc_exact_evals": (i32, [vp, c.POINTER(u64), i32]),
         "satmc_mc_step": (i32, [vp, f32p, f32p, u32, f32p, u32, f32p, f32p, f32p, f32p, f32p, f32p, i32, vp,
                                 i32, i32, i32, i32, u64, u32]),
         "satmc_write_collision_probability": (i32, [vp, f32p, i32, i32]),
+        "satmc_adaptive_run": (i32, [vp, f32p, f32p, u32, f32p, u32, f32p, f32p, f32p, i32, f32p, f32p, i32, i32, i32, i32,
+                                     i32, u64, u32, f32p, vp, c.POINTER(i32), c.POINTER(c.c_longlong)]),
+        "satmc_sample_positions": (i32, [vp, f32p, u32, f32p, u32, i32, c.c_float, c.c_float, u64, u32, f32p, f32p, f32p]),
+        "satmc_device_alloc": (i32, [vp, c.POINTER(vp), c.c_size_t]),
+        "satmc_device_free": (i32, [vp, vp]),
+        "satmc_upload": (i32, [vp, vp, vp, c.c_size_t]),
+        "satmc_download": (i32, [vp, vp, vp, c.c_size_t]),
         "satmc_count_fused_host": (i32, [vp, vp, u64, u64, u64, u64, u32, vp, u32]),
         "satmc_count_streamed_host": (i32, [vp, vp, u64, f32p, u64, u64, i32, u64, vp, u32]),
         "satmc_collision_probability_host": (i32, [vp, vp, u64, u64, u64, f32p]),
@@ -190,8 +198,8 @@ class Context:
         self._check(self._lib.satmc_decide_streamed(self._h, _ptr(d_pair), _ptr(d_z), ldz, ndof, n_samples,
                                                     _ptr(d_out), flags))
 
-    def fused_normals(self, seed, pair_id, sample_offset, n, d_z, ldz):
-        self._check(self._lib.satmc_fused_normals(self._h, seed, pair_id, sample_offset, n, _ptr(d_z), ldz))
+    def fused_normals(self, seed, pair_id, sample_offset, n, ndof, d_z, ldz):
+        self._check(self._lib.satmc_fused_normals(self._h, seed, pair_id, sample_offset, n, ndof, _ptr(d_z), ldz))
 
     def philox_blocks(self, d_ctr, n, key0, key1, d_out):
         self._check(self._lib.satmc_philox_blocks(self._h, _ptr(d_ctr), n, key0, key1, _ptr(d_out)))
@@ -207,6 +215,24 @@ class Context:
                                             _ptr(d_cps), _ptr(d_accuracy_bins), _ptr(d_bin_accuracy),
                                             n_accuracy_bins, _ptr(d_done), iteration, n_samples, n_batch, num_left,
                                             seed, stream_id_offset))
+
+    def adaptive_run(self, d_robot_base, d_poses, n_poses, d_std_devs, n_std, d_pose_idxs, d_std_dev_idxs, d_positions,
+                     n_pairs, d_accuracy_bins, d_bin_accuracy, n_accuracy_bins, max_samples, n_batch_small, switch_at,
+                     n_batch_large, seed, d_cp_out, d_n_samples_out=None, stream_id_offset=0):
+        """Returns (iterations, samples_drawn)."""
+        it, drawn = ctypes.c_int(0), ctypes.c_longlong(0)
+        self._check(self._lib.satmc_adaptive_run(self._h, _ptr(d_robot_base), _ptr(d_poses), n_poses, _ptr(d_std_devs), n_std,
+                                                 _ptr(d_pose_idxs), _ptr(d_std_dev_idxs), _ptr(d_positions), n_pairs,
+                                                 _ptr(d_accuracy_bins), _ptr(d_bin_accuracy), n_accuracy_bins, max_samples,
+                                                 n_batch_small, switch_at, n_batch_large, seed, stream_id_offset,
+                                                 _ptr(d_cp_out), _ptr(d_n_samples_out), ctypes.byref(it), ctypes.byref(drawn)))
+        return int(it.value), int(drawn.value)
+
+    def sample_positions(self, d_poses, n_poses, d_std_devs, n_std, n, r_offset, spread, seed, d_positions, d_pose_idxs,
+                         d_std_dev_idxs, stream_id_offset=0):
+        self._check(self._lib.satmc_sample_positions(self._h, _ptr(d_poses), n_poses, _ptr(d_std_devs), n_std, n, r_offset,
+                                                     spread, seed, stream_id_offset, _ptr(d_positions), _ptr(d_pose_idxs),
+                                                     _ptr(d_std_dev_idxs)))
 
     def write_collision_probability(self, d_counts, n_done, n_samples):
         self._check(self._lib.satmc_write_collision_probability(self._h, _ptr(d_counts), n_done, n_samples))

@@ -24,8 +24,14 @@ namespace satmc {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-#ifndef SATMC_MIN_BLOCKS
-#define SATMC_MIN_BLOCKS 2
+// resident blocks per SM the register allocator aims for: the fused loop is FMA-pipe bound and wants
+// registers (2 x 256 threads at 128 regs), the streamed loop is latency bound and wants warps
+// (measured on B200: fused 254 vs 246 Gtests/s, streamed 3-DoF 3.8 vs 4.9 TB/s for 2 vs 4 blocks)
+#ifndef SATMC_MIN_BLOCKS_FUSED
+#define SATMC_MIN_BLOCKS_FUSED 2
+#endif
+#ifndef SATMC_MIN_BLOCKS_STREAMED
+#define SATMC_MIN_BLOCKS_STREAMED 4
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -33,6 +39,7 @@ constexpr int kWarps = kThreads / 32;
 // ---------------------------------------------------------------------------------------------
 struct DirectSrc {
     const satmc_pair* pairs;
+    __device__ __forceinline__ uint64_t element(uint64_t slot) const { return slot; }
     __device__ __forceinline__ void load(uint64_t i, float v[12]) const {
         const float4* p = reinterpret_cast<const float4*>(pairs + i);   // 48 B, 16-B aligned
         const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
@@ -47,6 +54,8 @@ struct IndirectSrc {
     const float* robot_base; const float* poses; const float* std_devs;
     const float* pose_idxs; const float* std_dev_idxs; const float* positions;
     uint32_t n_poses, n_std;
+    const int* live;               // optional: slot -> pair id (device-side work list of unfinished pairs)
+    __device__ __forceinline__ uint64_t element(uint64_t slot) const { return live ? (uint64_t)__ldg(live + slot) : slot; }
     __device__ __forceinline__ void load(uint64_t i, float v[12]) const {
         uint32_t pi = (uint32_t)(int)__ldg(pose_idxs + i);
         uint32_t si = (uint32_t)(int)__ldg(std_dev_idxs + i);
@@ -79,32 +88,53 @@ struct CountParams {
     PhiloxKeys keys;           // fused: round keys, read straight from the constant bank
 };
 
-// Cold path of the fused sampler: regenerate the normals of sample s (counter-based, so nothing
-// has to stay live across the hot loop) and decide with the exact reference arithmetic.
-template <int NDOF>
-__device__ __noinline__ unsigned fused_exact(const PairConst& P, const float* robot, uint64_t s, uint32_t pid,
-                                             const PhiloxKeys& K, unsigned long long* exact_evals)
+// Slow, general evaluation of the slots of one sample group selected by slot_mask (bit t = sample
+// 4g+t): used for the ragged ends of a chunk and whenever the hot loop meets a sample the screening
+// pass cannot decide.  The normals are regenerated from the counter, so the hot loop keeps nothing
+// alive for it.
+template <int D>
+__device__ __noinline__ unsigned fused_group_slow(const PairConst& P, const float* robot, uint64_t g, unsigned slot_mask,
+                                                  uint32_t pid, const PhiloxKeys& K, unsigned long long* exact_evals)
 {
-    float z0, z1, z2, z3, z4 = 0.0f;
-    normals4<NDOF == 5>((uint32_t)s, (uint32_t)(s >> 32), pid, K, z0, z1, z2, z3);
-    if (NDOF == 5) z4 = normal5th((uint32_t)s, (uint32_t)(s >> 32), pid, K);
-    if (exact_evals) atomicAdd(exact_evals, 1ull);
-    return (unsigned)exact_decide(robot, P.ow, P.oh, P.sd_x, P.sd_y, P.sd_t, P.sd_w, P.sd_h, z0, z1, z2, z3, z4);
+    float n[4 * D];
+    group_normals<D>((uint32_t)g, (uint32_t)(g >> 32), pid, K, n);
+    unsigned cnt = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        if (!(slot_mask & (1u << t))) continue;
+        const float z3 = (D == 5) ? n[D * t + 3] : 0.0f, z4 = (D == 5) ? n[D * t + 4] : 0.0f;
+        float hmin;
+        const float m = screen_gap<D>(P, n[D * t], n[D * t + 1], n[D * t + 2], z3, z4, hmin);
+        unsigned hit = __float_as_uint(m) >> 31;
+        if (!screen_decided<D>(P, m, hmin)) {
+            hit = (unsigned)exact_decide(robot, P.ow, P.oh, P.sd_x, P.sd_y, P.sd_t, P.sd_w, P.sd_h, n[D * t], n[D * t + 1],
+                                         n[D * t + 2], z3, z4);
+            if (exact_evals) atomicAdd(exact_evals, 1ull);
+        }
+        cnt += hit;
+    }
+    return cnt;
 }
 
-// one sample of the fused path
-template <int NDOF>
-__device__ __forceinline__ unsigned fused_sample(const PairConst& P, const float* robot, uint64_t s, uint32_t pid,
-                                                 const PhiloxKeys& K, unsigned long long* exact_evals)
+// hot path: all four samples of group g
+template <int D>
+__device__ __forceinline__ unsigned fused_group(const PairConst& P, const float* robot, uint64_t g, uint32_t pid,
+                                                const PhiloxKeys& K, unsigned long long* exact_evals)
 {
-    float z0, z1, z2, z3, z4 = 0.0f, hmin;
-    normals4<NDOF == 5>((uint32_t)s, (uint32_t)(s >> 32), pid, K, z0, z1, z2, z3);
-    if (NDOF == 5) z4 = normal5th((uint32_t)s, (uint32_t)(s >> 32), pid, K);
-    const float m = screen_gap<NDOF>(P, z0, z1, z2, z3, z4, hmin);
-    unsigned hit = __float_as_uint(m) >> 31;                        // m < 0 (m = -0 / NaN are undecided anyway)
-    if (!screen_decided<NDOF>(P, m, hmin))                          // undecided (or NaN): exact arithmetic
-        hit = fused_exact<NDOF>(P, robot, s, pid, K, exact_evals);
-    return hit;
+    float n[4 * D];
+    group_normals<D>((uint32_t)g, (uint32_t)(g >> 32), pid, K, n);
+    unsigned cnt = 0;
+    bool decided = true;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const float z3 = (D == 5) ? n[D * t + 3] : 0.0f, z4 = (D == 5) ? n[D * t + 4] : 0.0f;
+        float hmin;
+        const float m = screen_gap<D>(P, n[D * t], n[D * t + 1], n[D * t + 2], z3, z4, hmin);
+        cnt += __float_as_uint(m) >> 31;                            // m < 0 (m = -0 / NaN are undecided anyway)
+        decided = decided && screen_decided<D>(P, m, hmin);
+    }
+    if (!decided) cnt = fused_group_slow<D>(P, robot, g, 0xFu, pid, K, exact_evals);   // rare: redo the group
+    return cnt;
 }
 
 // one sample of the streamed path (normals supplied)
@@ -126,19 +156,28 @@ __device__ __forceinline__ unsigned streamed_sample(const PairConst& P, const fl
     return hit;
 }
 
-template <int NDOF>
-__device__ __forceinline__ unsigned fused_chunk(const PairConst& P, const float* robot, uint64_t s_begin, uint64_t len,
+// samples [b, e) (absolute indices) of one pair: full groups go through the hot loop, the at most two
+// ragged groups at the ends through the slow path on lanes 0 and 1
+template <int D>
+__device__ __forceinline__ unsigned fused_chunk(const PairConst& P, const float* robot, uint64_t b, uint64_t e,
                                                 uint32_t pid, const PhiloxKeys& K, int lane,
                                                 unsigned long long* exact_evals)
 {
     unsigned cnt = 0;
-    uint64_t i = (uint64_t)lane;
-    // two independent samples per trip: hides the serial Philox round chain
-    for (; i + 32 < len; i += 64) {
-        cnt += fused_sample<NDOF>(P, robot, s_begin + i, pid, K, exact_evals);
-        cnt += fused_sample<NDOF>(P, robot, s_begin + i + 32, pid, K, exact_evals);
+    const uint64_t g_lo = (b + 3) >> 2, g_hi = e >> 2;
+    if (g_hi < g_lo) {                                              // whole range inside one group
+        if (lane == 0) {
+            const unsigned mask = (0xFu << (unsigned)(b & 3)) & (0xFu >> (4 - (unsigned)(e & 3))) & 0xFu;
+            cnt = fused_group_slow<D>(P, robot, b >> 2, mask, pid, K, exact_evals);
+        }
+        return cnt;
     }
-    if (i < len) cnt += fused_sample<NDOF>(P, robot, s_begin + i, pid, K, exact_evals);
+    for (uint64_t g = g_lo + (uint64_t)lane; g < g_hi; g += 32)
+        cnt += fused_group<D>(P, robot, g, pid, K, exact_evals);
+    if (lane == 0 && (b & 3))
+        cnt += fused_group_slow<D>(P, robot, b >> 2, (0xFu << (unsigned)(b & 3)) & 0xFu, pid, K, exact_evals);
+    if (lane == 1 && (e & 3))
+        cnt += fused_group_slow<D>(P, robot, g_hi, 0xFu >> (4 - (unsigned)(e & 3)), pid, K, exact_evals);
     return cnt;
 }
 
@@ -177,7 +216,7 @@ __device__ __forceinline__ unsigned streamed_chunk(const PairConst& P, const flo
 }
 
 template <class Src, bool STREAMED>
-__global__ void __launch_bounds__(kThreads, SATMC_MIN_BLOCKS) k_count(const __grid_constant__ Src src, const __grid_constant__ CountParams p)
+__global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED : SATMC_MIN_BLOCKS_FUSED) k_count(const __grid_constant__ Src src, const __grid_constant__ CountParams p)
 {
     __shared__ float s_robot[kWarps][8];
     __shared__ unsigned s_part[kWarps];
@@ -188,7 +227,8 @@ __global__ void __launch_bounds__(kThreads, SATMC_MIN_BLOCKS) k_count(const __gr
         const uint64_t pair = item / p.n_chunks;
         const uint32_t chunk_id = (uint32_t)(item - pair * p.n_chunks);
         float v[12];
-        src.load(pair, v);
+        const uint64_t elem = src.element(pair);                    // array index and Philox stream of this slot
+        src.load(elem, v);
         PairConst P;
         pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
         if (p.flags & SATMC_EXACT_ONLY) { P.eps = CUDART_INF_F; P.eps_b = CUDART_INF_F; }
@@ -204,11 +244,11 @@ __global__ void __launch_bounds__(kThreads, SATMC_MIN_BLOCKS) k_count(const __gr
             cnt = (p.ndof == 5) ? streamed_chunk<5>(P, s_robot[warp], z, p.ldz, c_len, p.vec_ok, lane, ev)
                                 : streamed_chunk<3>(P, s_robot[warp], z, p.ldz, c_len, p.vec_ok, lane, ev);
         } else {
-            const uint32_t pid = p.pair_id_offset + (uint32_t)pair;
+            const uint32_t pid = p.pair_id_offset + (uint32_t)elem;
             const uint64_t s_begin = p.sample_offset + c_begin;
             const bool dof3 = (v[10] == 0.0f) && (v[11] == 0.0f);
-            cnt = dof3 ? fused_chunk<3>(P, s_robot[warp], s_begin, c_len, pid, p.keys, lane, ev)
-                       : fused_chunk<5>(P, s_robot[warp], s_begin, c_len, pid, p.keys, lane, ev);
+            cnt = dof3 ? fused_chunk<3>(P, s_robot[warp], s_begin, s_begin + c_len, pid, p.keys, lane, ev)
+                       : fused_chunk<5>(P, s_robot[warp], s_begin, s_begin + c_len, pid, p.keys, lane, ev);
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (p.block_uniform) {
@@ -256,14 +296,21 @@ __global__ void k_decide(satmc_pair const* pair, const float* __restrict__ z, ui
     }
 }
 
+// normals of samples [offset, offset+n) of stream pid, D planes (D = 3 or 5); one thread per group
+template <int D>
 __global__ void k_fused_normals(const __grid_constant__ PhiloxKeys K, uint32_t pid, uint64_t offset, uint64_t n, float* z, uint64_t ldz)
 {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t s = offset + i;
-        float z0, z1, z2, z3;
-        normals4<true>((uint32_t)s, (uint32_t)(s >> 32), pid, K, z0, z1, z2, z3);
-        const float z4 = normal5th((uint32_t)s, (uint32_t)(s >> 32), pid, K);
-        z[i] = z0; z[ldz + i] = z1; z[2 * ldz + i] = z2; z[3 * ldz + i] = z3; z[4 * ldz + i] = z4;
+    const uint64_t g0 = offset >> 2, g1 = (offset + n + 3) >> 2;
+    for (uint64_t g = g0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < g1; g += (uint64_t)gridDim.x * blockDim.x) {
+        float nn[4 * D];
+        group_normals<D>((uint32_t)g, (uint32_t)(g >> 32), pid, K, nn);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const uint64_t s = 4 * g + t;
+            if (s < offset || s >= offset + n) continue;
+#pragma unroll
+            for (int k = 0; k < D; k++) z[k * ldz + (s - offset)] = nn[D * t + k];
+        }
     }
 }
 
@@ -301,18 +348,81 @@ __device__ __forceinline__ float calc_slack(int n, int k)
 }
 
 __global__ void k_ztest_tail(const unsigned long long* __restrict__ hits, float* cps, const float* __restrict__ bins,
-                             const float* __restrict__ bin_acc, int n_bins, int* done, int n_samples, int num_left)
+                             const float* __restrict__ bin_acc, int n_bins, int* done, int n_samples, int num_left,
+                             const int* __restrict__ live)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= num_left) return;
-    const int k = (int)cps[g] + (int)hits[g];
+    const int e = live ? live[g] : g;
+    const int k = (int)cps[e] + (int)hits[g];
     const float slack = calc_slack(n_samples, k);
     const float p = (float)k / (float)n_samples;
     int bin = 0;
     for (int i = 0; i + 1 < n_bins; i++)
         if (p >= bins[i] && p <= bins[i + 1]) bin = i;
-    done[g] = (slack <= bin_acc[bin]) ? 1 : 0;
-    cps[g] = (float)k;
+    done[e] = (slack <= bin_acc[bin]) ? 1 : 0;
+    cps[e] = (float)k;
+}
+
+// ---- adaptive scheduler (replaces thrust::count + sort_by_key + tail copies, ztest.cu:359-371) ----
+__global__ void k_iota(int* a, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
+}
+
+// Splits the live list: finished pairs get their probability written in place (count / n_samples, the
+// arithmetic of write_collision_probability utils.cu:210-215) and leave the list, the rest are appended
+// to live_out.  Warp-aggregated append: one atomic per warp.
+__global__ void k_compact_live(const int* __restrict__ live_in, int num_left, const int* __restrict__ done,
+                               const float* __restrict__ counts, int n_samples, float* cp_out, int* n_samples_out,
+                               int* live_out, int* n_out, int finalize_all)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < num_left;
+    int e = 0; bool keep = false;
+    if (valid) {
+        e = live_in[i];
+        const bool fin = finalize_all || done[e] != 0;
+        if (fin) {
+            cp_out[e] = counts[e] / (float)n_samples;
+            if (n_samples_out) n_samples_out[e] = n_samples;
+        }
+        keep = !fin;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(n_out, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (keep) live_out[base + __popc(m & ((1u << lane) - 1u))] = e;
+}
+
+// iteration-0 draw of generate_dataset (generate_dataset.cu:207-219): pose index, std-dev index and a
+// robot position on the ring prior around the obstacle.  Philox stream = stream_id_offset + g, counter
+// block 0xffffffff (disjoint from the sample groups).
+__global__ void k_sample_positions(const __grid_constant__ PhiloxKeys K, const float* __restrict__ poses, uint32_t n_poses,
+                                   const float* __restrict__ std_devs, uint32_t n_std, int n, float r_offset, float spread,
+                                   uint32_t stream_id_offset, float* positions, float* pose_idxs, float* std_dev_idxs)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    uint32_t w[4], w2[4];
+    philox4x32_10(0xffffffffu, 0xffffffffu, stream_id_offset + (uint32_t)g, 0u, K, w);
+    philox4x32_10(0xffffffffu, 0xffffffffu, stream_id_offset + (uint32_t)g, 1u, K, w2);
+    const uint32_t pi = w[0] % n_poses, si = w[1] % n_std;                    // curand() % n   (:208-209)
+    const float pw = poses[3 * (size_t)pi], ph = poses[3 * (size_t)pi + 1];
+    const float sx = std_devs[5 * (size_t)si], sy = std_devs[5 * (size_t)si + 1];
+    const float uni = ((float)(w[2] >> 8) + 1.0f) * 5.9604645e-8f;            // curand_uniform: (0, 1]   (:213)
+    const float theta = (float)(uni * 2 * 3.14159265358979323846);
+    float nz, unused;
+    bm_pair(w2[0], w2[1], nz, unused);                                        // curand_normal            (:214)
+    const float shift = nz * ((sy + sx) / 2) * spread;
+    positions[2 * (size_t)g]     = (float)(cosf(theta) * ((pw / 2 + r_offset + 2.35 + sx) + shift));   // (:215)
+    positions[2 * (size_t)g + 1] = (float)(sinf(theta) * ((ph / 2 + r_offset + 2.35 + sy) + shift));   // (:216)
+    pose_idxs[g] = (float)pi;
+    std_dev_idxs[g] = (float)si;
 }
 
 __global__ void k_write_cp(float* counts, int n_done, int n_samples)
@@ -339,6 +449,7 @@ struct satmc_ctx {
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     int blocks_per_sm = 0;
+    int blocks_per_sm_streamed = 0;
     char err[512] = {0};
     uint64_t launches = 0;
     unsigned long long* d_exact_evals = nullptr;
@@ -419,8 +530,11 @@ int satmc_create(int device, void* stream, satmc_ctx** out)
     DeviceGuard g(device);
     int bps = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_count<DirectSrc, false>, kThreads, 0);
-    if (e != cudaSuccess || bps < 1) bps = 2;
+    if (e != cudaSuccess || bps < 1) bps = SATMC_MIN_BLOCKS_FUSED;
     ctx->blocks_per_sm = bps;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_count<DirectSrc, true>, kThreads, 0);
+    if (e != cudaSuccess || bps < 1) bps = SATMC_MIN_BLOCKS_STREAMED;
+    ctx->blocks_per_sm_streamed = bps;
     if (cudaMalloc(&ctx->d_exact_evals, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(ctx->d_exact_evals, 0, sizeof(unsigned long long)) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
@@ -496,7 +610,8 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
             CU(ctx, cudaMemsetAsync(p.hits, 0, p.n_pairs * sizeof(unsigned long long), ctx->stream));
         return SATMC_OK;
     }
-    const uint64_t resident_warps = (uint64_t)ctx->sm_count * ctx->blocks_per_sm * kWarps;
+    const int bps = STREAMED ? ctx->blocks_per_sm_streamed : ctx->blocks_per_sm;
+    const uint64_t resident_warps = (uint64_t)ctx->sm_count * bps * kWarps;
     const uint64_t target_items = resident_warps * 8;             // >= 8 items per resident warp when possible
     const uint64_t min_chunk = 2048;                              // 64 samples per lane: amortises the pair prologue
     uint64_t n_chunks = 1;
@@ -518,7 +633,7 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
     if (n_chunks > 1 && !(p.flags & SATMC_ACCUMULATE))
         CU(ctx, cudaMemsetAsync(p.hits, 0, p.n_pairs * sizeof(unsigned long long), ctx->stream));
     uint64_t blocks = (p.n_items + kWarps - 1) / kWarps;
-    const uint64_t max_blocks = (uint64_t)ctx->sm_count * ctx->blocks_per_sm;
+    const uint64_t max_blocks = (uint64_t)ctx->sm_count * bps;
     if (blocks > max_blocks) blocks = max_blocks;
     if (time_it) CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     k_count<Src, STREAMED><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
@@ -588,17 +703,19 @@ int satmc_decide_streamed(satmc_ctx* ctx, const satmc_pair* d_pair, const float*
     return SATMC_OK;
 }
 
-int satmc_fused_normals(satmc_ctx* ctx, uint64_t seed, uint32_t pair_id, uint64_t sample_offset, uint64_t n, float* d_z,
-                        uint64_t ldz)
+int satmc_fused_normals(satmc_ctx* ctx, uint64_t seed, uint32_t pair_id, uint64_t sample_offset, uint64_t n, int ndof,
+                        float* d_z, uint64_t ldz)
 {
     if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    if (ndof != 3 && ndof != 5) return fail(ctx, SATMC_ERR_INVALID, "ndof must be 3 or 5, got %d", ndof);
     if (!d_z || ldz < n) return fail(ctx, SATMC_ERR_INVALID, "bad output plane (null or ldz < n)");
     if (n == 0) return SATMC_OK;
     DeviceGuard g(ctx->device);
-    uint64_t blocks = (n + 255) / 256;
+    uint64_t blocks = (n / 4 + 256) / 256;
     if (blocks > (uint64_t)ctx->sm_count * 8) blocks = (uint64_t)ctx->sm_count * 8;
     PhiloxKeys K; philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), K);
-    k_fused_normals<<<(unsigned)blocks, 256, 0, ctx->stream>>>(K, pair_id, sample_offset, n, d_z, ldz);
+    if (ndof == 3) k_fused_normals<3><<<(unsigned)blocks, 256, 0, ctx->stream>>>(K, pair_id, sample_offset, n, d_z, ldz);
+    else           k_fused_normals<5><<<(unsigned)blocks, 256, 0, ctx->stream>>>(K, pair_id, sample_offset, n, d_z, ldz);
     CU(ctx, cudaGetLastError());
     ctx->launches++;
     return SATMC_OK;
@@ -630,13 +747,12 @@ int satmc_sat_corners(satmc_ctx* ctx, const float* d_r1, const float* d_r2, uint
     return SATMC_OK;
 }
 
-int satmc_mc_step(satmc_ctx* ctx, const float* d_robot_base, const float* d_poses, uint32_t n_poses, const float* d_std_devs,
-                  uint32_t n_std, const float* d_pose_idxs, const float* d_std_dev_idxs, const float* d_positions,
-                  float* d_cps, const float* d_accuracy_bins, const float* d_bin_accuracy, int n_accuracy_bins,
-                  int* d_done, int iteration, int n_samples, int n_batch, int num_left, uint64_t seed,
-                  uint32_t stream_id_offset)
+static int mc_step_impl(satmc_ctx* ctx, const float* d_robot_base, const float* d_poses, uint32_t n_poses,
+                        const float* d_std_devs, uint32_t n_std, const float* d_pose_idxs, const float* d_std_dev_idxs,
+                        const float* d_positions, float* d_cps, const float* d_accuracy_bins, const float* d_bin_accuracy,
+                        int n_accuracy_bins, int* d_done, int n_samples, int n_batch, int num_left, uint64_t seed,
+                        uint32_t stream_id_offset, const int* d_live)
 {
-    (void)iteration;
     if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
     if (!d_robot_base || !d_poses || !d_std_devs || !d_pose_idxs || !d_std_dev_idxs || !d_positions || !d_cps ||
         !d_accuracy_bins || !d_bin_accuracy || !d_done)
@@ -653,15 +769,148 @@ int satmc_mc_step(satmc_ctx* ctx, const float* d_robot_base, const float* d_pose
     p.n_pairs = (uint64_t)num_left; p.n_samples = (uint64_t)n_batch; p.sample_offset = (uint64_t)(n_samples - n_batch);
     p.pair_id_offset = stream_id_offset; philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), p.keys); p.flags = 0;
     p.hits = reinterpret_cast<unsigned long long*>(d_hits); p.exact_evals = ctx->d_exact_evals;
-    IndirectSrc src{d_robot_base, d_poses, d_std_devs, d_pose_idxs, d_std_dev_idxs, d_positions, n_poses, n_std};
+    IndirectSrc src{d_robot_base, d_poses, d_std_devs, d_pose_idxs, d_std_dev_idxs, d_positions, n_poses, n_std, d_live};
     if (n_batch == 0) CU(ctx, cudaMemsetAsync(d_hits, 0, (size_t)num_left * sizeof(unsigned long long), ctx->stream));
     rc = launch_count<IndirectSrc, false>(ctx, src, p, ctx->profiling);
     if (rc) return rc;
     k_ztest_tail<<<(num_left + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<unsigned long long*>(d_hits), d_cps,
                                                                    d_accuracy_bins, d_bin_accuracy, n_accuracy_bins, d_done,
-                                                                   n_samples, num_left);
+                                                                   n_samples, num_left, d_live);
     CU(ctx, cudaGetLastError());
     ctx->launches++;
+    return SATMC_OK;
+}
+
+int satmc_mc_step(satmc_ctx* ctx, const float* d_robot_base, const float* d_poses, uint32_t n_poses, const float* d_std_devs,
+                  uint32_t n_std, const float* d_pose_idxs, const float* d_std_dev_idxs, const float* d_positions,
+                  float* d_cps, const float* d_accuracy_bins, const float* d_bin_accuracy, int n_accuracy_bins,
+                  int* d_done, int iteration, int n_samples, int n_batch, int num_left, uint64_t seed,
+                  uint32_t stream_id_offset)
+{
+    (void)iteration;
+    return mc_step_impl(ctx, d_robot_base, d_poses, n_poses, d_std_devs, n_std, d_pose_idxs, d_std_dev_idxs, d_positions,
+                        d_cps, d_accuracy_bins, d_bin_accuracy, n_accuracy_bins, d_done, n_samples, n_batch, num_left, seed,
+                        stream_id_offset, nullptr);
+}
+
+int satmc_adaptive_run(satmc_ctx* ctx, const float* d_robot_base, const float* d_poses, uint32_t n_poses,
+                       const float* d_std_devs, uint32_t n_std, const float* d_pose_idxs, const float* d_std_dev_idxs,
+                       const float* d_positions, int n_pairs, const float* d_accuracy_bins, const float* d_bin_accuracy,
+                       int n_accuracy_bins, int max_samples, int n_batch_small, int switch_at, int n_batch_large,
+                       uint64_t seed, uint32_t stream_id_offset, float* d_cp_out, int* d_n_samples_out,
+                       int* iterations_out, long long* samples_drawn_out)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    if (!d_cp_out) return fail(ctx, SATMC_ERR_INVALID, "d_cp_out is NULL");
+    if (n_pairs < 0 || n_batch_small <= 0 || n_batch_large <= 0 || max_samples <= 0)
+        return fail(ctx, SATMC_ERR_INVALID, "bad schedule (n_pairs %d, n_batch %d/%d, max_samples %d)", n_pairs, n_batch_small,
+                    n_batch_large, max_samples);
+    if (iterations_out) *iterations_out = 0;
+    if (samples_drawn_out) *samples_drawn_out = 0;
+    if (n_pairs == 0) return SATMC_OK;
+    DeviceGuard g(ctx->device);
+    // work buffers: counts (float, as the reference keeps them), done flags, two live lists, a counter
+    const size_t n = (size_t)n_pairs;
+    void* base = nullptr;
+    const size_t bytes = n * (sizeof(float) + 3 * sizeof(int)) + 256;
+    int rc = scratch(ctx, 1, bytes, &base);
+    if (rc) return rc;
+    float* d_counts = reinterpret_cast<float*>(base);
+    int* d_done = reinterpret_cast<int*>(d_counts + n);
+    int* d_live[2] = {d_done + n, d_done + 2 * n};
+    int* d_n = d_done + 3 * n;
+    CU(ctx, cudaMemsetAsync(d_counts, 0, n * sizeof(float), ctx->stream));
+    k_iota<<<(n_pairs + 255) / 256, 256, 0, ctx->stream>>>(d_live[0], n_pairs);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    int num_left = n_pairs, n_samples = 0, iter = 0, cur = 0;
+    long long drawn = 0;
+    while (num_left > 0 && n_samples < max_samples) {                       // ztest.cu:328, generate_dataset.cu:425
+        const int n_batch = (n_samples < switch_at) ? n_batch_small : n_batch_large;    // generate_dataset.cu:427-430
+        n_samples += n_batch;
+        rc = mc_step_impl(ctx, d_robot_base, d_poses, n_poses, d_std_devs, n_std, d_pose_idxs, d_std_dev_idxs, d_positions,
+                          d_counts, d_accuracy_bins, d_bin_accuracy, n_accuracy_bins, d_done, n_samples, n_batch, num_left,
+                          seed, stream_id_offset, d_live[cur]);
+        if (rc) return rc;
+        drawn += (long long)num_left * n_batch;
+        CU(ctx, cudaMemsetAsync(d_n, 0, sizeof(int), ctx->stream));
+        k_compact_live<<<(num_left + 255) / 256, 256, 0, ctx->stream>>>(d_live[cur], num_left, d_done, d_counts, n_samples,
+                                                                         d_cp_out, d_n_samples_out, d_live[cur ^ 1], d_n, 0);
+        CU(ctx, cudaGetLastError());
+        ctx->launches++;
+        CU(ctx, cudaMemcpyAsync(&num_left, d_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));                       // the loop condition needs the count
+        cur ^= 1;
+        iter++;
+    }
+    if (num_left > 0) {                                                     // hit max_samples: ztest.cu:376-385
+        CU(ctx, cudaMemsetAsync(d_n, 0, sizeof(int), ctx->stream));
+        k_compact_live<<<(num_left + 255) / 256, 256, 0, ctx->stream>>>(d_live[cur], num_left, d_done, d_counts, n_samples,
+                                                                         d_cp_out, d_n_samples_out, d_live[cur ^ 1], d_n, 1);
+        CU(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    if (iterations_out) *iterations_out = iter;
+    if (samples_drawn_out) *samples_drawn_out = drawn;
+    return SATMC_OK;
+}
+
+int satmc_sample_positions(satmc_ctx* ctx, const float* d_poses, uint32_t n_poses, const float* d_std_devs, uint32_t n_std,
+                           int n, float r_offset, float spread, uint64_t seed, uint32_t stream_id_offset,
+                           float* d_positions, float* d_pose_idxs, float* d_std_dev_idxs)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    if (!d_poses || !d_std_devs || !d_positions || !d_pose_idxs || !d_std_dev_idxs || n_poses == 0 || n_std == 0)
+        return fail(ctx, SATMC_ERR_INVALID, "null pointer or empty table");
+    if (n <= 0) return SATMC_OK;
+    DeviceGuard g(ctx->device);
+    PhiloxKeys K; philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), K);
+    k_sample_positions<<<(n + 255) / 256, 256, 0, ctx->stream>>>(K, d_poses, n_poses, d_std_devs, n_std, n, r_offset, spread,
+                                                                 stream_id_offset, d_positions, d_pose_idxs, d_std_dev_idxs);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    return SATMC_OK;
+}
+
+// ---- device memory helpers so that host programs need no CUDA headers -------------------------------
+int satmc_device_alloc(satmc_ctx* ctx, void** out, size_t bytes)
+{
+    if (!ctx || !out) return fail(ctx, SATMC_ERR_INVALID, "null argument");
+    DeviceGuard g(ctx->device);
+    if (cudaMalloc(out, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError(); *out = nullptr;
+        return fail(ctx, SATMC_ERR_NOMEM, "cudaMalloc of %zu bytes failed", bytes);
+    }
+    return SATMC_OK;
+}
+
+int satmc_device_free(satmc_ctx* ctx, void* p)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    DeviceGuard g(ctx->device);
+    if (p) CU(ctx, cudaFree(p));
+    return SATMC_OK;
+}
+
+int satmc_upload(satmc_ctx* ctx, void* d_dst, const void* h_src, size_t bytes)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    if (bytes == 0) return SATMC_OK;
+    if (!d_dst || !h_src) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
+    DeviceGuard g(ctx->device);
+    CU(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SATMC_OK;
+}
+
+int satmc_download(satmc_ctx* ctx, void* h_dst, const void* d_src, size_t bytes)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    if (bytes == 0) return SATMC_OK;
+    if (!h_dst || !d_src) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
+    DeviceGuard g(ctx->device);
+    CU(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     return SATMC_OK;
 }
 

@@ -171,7 +171,7 @@ __device__ __forceinline__ void pair_const_init(PairConst& P, float rx, float ry
     P.nkx0 = -(sd_x * ca); P.nky0 = -(sd_y * sa);
     P.kx1 = sd_x * sa;     P.nky1 = -(sd_y * ca);
     P.a0 = 0.5f * fabsf(rw); P.a1 = 0.5f * fabsf(rh);
-    P.b0 = 0.5f * ow;        P.b1 = 0.5f * oh;
+    P.b0 = 0.5f * fabsf(ow); P.b1 = 0.5f * fabsf(oh);
     P.hw = 0.5f * sd_w;      P.hh = 0.5f * sd_h;
     P.ow = ow; P.oh = oh; P.sd_x = sd_x; P.sd_y = sd_y; P.sd_t = sd_t; P.sd_w = sd_w; P.sd_h = sd_h;
     screen_eps(rx, ry, P.a0, P.a1, P.b0, P.b1, sd_x, sd_y, sd_t, sd_w, sd_h, P.eps_a, P.eps_b);
@@ -198,7 +198,8 @@ __device__ __forceinline__ float screen_gap(const PairConst& P, float z0, float 
     const float C = fabsf(fmaf(P.ca, c, P.sa * s));
     const float S = fabsf(fmaf(P.sa, c, -(P.ca * s)));
     float hx = P.b0, hy = P.b1;
-    if (NDOF == 5) { hx = fmaf(z3, P.hw, hx); hy = fmaf(z4, P.hh, hy); }
+    // a perturbation past -width flips the corner order but spans the same rectangle: |half extent|
+    if (NDOF == 5) { hx = fabsf(fmaf(z3, P.hw, hx)); hy = fabsf(fmaf(z4, P.hh, hy)); }
     hmin = fminf(hx, hy);
     const float tb0 = fabsf(ub0) - fmaf(P.a0, C, fmaf(P.a1, S, hx));
     const float tb1 = fabsf(ub1) - fmaf(P.a0, S, fmaf(P.a1, C, hy));

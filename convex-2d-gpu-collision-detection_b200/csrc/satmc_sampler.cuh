@@ -5,9 +5,12 @@
 // stateless generator: normals of sample s of stream (pair) p under seed k are a pure function of
 // (k, p, s), so samples never touch HBM and any partition of the work gives identical results.
 //
-//   Philox4x32-10, key = (seed_lo, seed_hi), counter = (s_lo, s_hi, p, j)
-//     j = 0 -> four 32-bit words -> two Box-Muller pairs -> z0 (x), z1 (y), z2 (theta), z3 (w)
-//     j = 1 -> one more pair                            -> z4 (h)          (5-DoF pairs only)
+//   Samples are drawn in groups of four consecutive sample indices so that every Philox word and every
+//   Box-Muller output is used (IMAD.WIDE runs at quarter rate on sm_100a: Philox is the scarce resource):
+//     group g = s >> 2 holds samples 4g..4g+3, each needing D normals (D = 3: x,y,theta; D = 5: +w,h)
+//     Philox4x32-10, key = (seed_lo, seed_hi), counter = (g_lo, g_hi, p, j), j = 0..D-1
+//       -> 4 words -> two Box-Muller pairs -> normals n[4j..4j+3] = (cos0, sin0, cos1, sin1)
+//     sample 4g+t uses n[D*t .. D*t+D-1] in the order x, y, theta[, w, h].
 //   Box-Muller on words (a, b):
 //     U     = RN((a + 0.5) * 2^-32)             (float in [2^-33, 1]; exact for small values, so the tail
 //                                                 has 32-bit resolution: largest radius sqrt(2*33*ln2) = 6.76,
@@ -81,26 +84,25 @@ __device__ __forceinline__ float bm_angle(uint32_t b)
     return __fmaf_rn(f, 6.283185307179586f, -6.283184932672558f);              // 2pi*(f - 1 + 2^-24)
 }
 
-// z0..z3 of sample (s, stream p); z3 only if WANT4
-template <bool WANT4>
-__device__ __forceinline__ void normals4(uint32_t s_lo, uint32_t s_hi, uint32_t p, const PhiloxKeys& K,
-                                         float& z0, float& z1, float& z2, float& z3)
+// both normals of one Box-Muller pair
+__device__ __forceinline__ void bm_pair(uint32_t a, uint32_t b, float& n_cos, float& n_sin)
 {
-    uint32_t w[4];
-    philox4x32_10(s_lo, s_hi, p, 0u, K, w);
-    const float ra = bm_radius(w[0]), pa = bm_angle(w[1]);
-    const float rb = bm_radius(w[2]), pb = bm_angle(w[3]);
-    z0 = __fmul_rn(ra, mufu_cos(pa));
-    z1 = __fmul_rn(ra, mufu_sin(pa));
-    z2 = __fmul_rn(rb, mufu_cos(pb));
-    z3 = WANT4 ? __fmul_rn(rb, mufu_sin(pb)) : 0.0f;
+    const float r = bm_radius(a), ang = bm_angle(b);
+    n_cos = __fmul_rn(r, mufu_cos(ang));
+    n_sin = __fmul_rn(r, mufu_sin(ang));
 }
 
-__device__ __forceinline__ float normal5th(uint32_t s_lo, uint32_t s_hi, uint32_t p, const PhiloxKeys& K)
+// the 4*D normals of group (g_lo, g_hi) of stream p
+template <int D>
+__device__ __forceinline__ void group_normals(uint32_t g_lo, uint32_t g_hi, uint32_t p, const PhiloxKeys& K, float n[4 * D])
 {
-    uint32_t w[4];
-    philox4x32_10(s_lo, s_hi, p, 1u, K, w);
-    return __fmul_rn(bm_radius(w[0]), mufu_cos(bm_angle(w[1])));
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        uint32_t w[4];
+        philox4x32_10(g_lo, g_hi, p, (uint32_t)j, K, w);
+        bm_pair(w[0], w[1], n[4 * j], n[4 * j + 1]);
+        bm_pair(w[2], w[3], n[4 * j + 2], n[4 * j + 3]);
+    }
 }
 
 }  // namespace satmc

@@ -93,7 +93,8 @@ float satmc_last_kernel_ms(const satmc_ctx* ctx);
  *             monte_carlo_sample_collision_dataset_uniform ztest.cu:151-155
  *             (= compute_collision_probability.cu:135-139, generate_dataset.cu:238-242)
  * d_hits[i] = #{ s in [sample_offset, sample_offset + n_samples) : pair i collides on sample s }.
- * The normals of sample s of pair i depend only on (seed, pair_id_offset + i, s): any split of the
+ * The normals of sample s of pair i depend only on (seed, pair_id_offset + i, s) and on whether the
+ * pair has shape variance: any split of the
  * pair range or the sample range over calls, streams, GPUs or ranks gives bit-identical totals.
  * Pairs with sd_w == sd_h == 0 take a 3-normal path (x, y, theta), others draw all five. */
 int satmc_count_fused(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pairs,
@@ -115,10 +116,11 @@ int satmc_decide_streamed(satmc_ctx* ctx, const satmc_pair* d_pair, const float*
                           int ndof, uint64_t n_samples, uint8_t* d_out, uint32_t flags);
 
 /* The normals the fused path uses for samples [sample_offset, sample_offset+n) of pair `pair_id`,
- * written as 5 SoA planes d_z[k*ldz + s].  Feeding them to satmc_count_streamed / the oracle must
- * reproduce satmc_count_fused's count exactly. */
+ * written as ndof SoA planes d_z[k*ldz + s].  ndof must be the pair's own: 3 if its sd_w == sd_h == 0,
+ * else 5 (the two kinds of pair consume the Philox stream differently).  Feeding the planes to
+ * satmc_count_streamed / the oracle must reproduce satmc_count_fused's count exactly. */
 int satmc_fused_normals(satmc_ctx* ctx, uint64_t seed, uint32_t pair_id, uint64_t sample_offset,
-                        uint64_t n, float* d_z, uint64_t ldz);
+                        uint64_t n, int ndof, float* d_z, uint64_t ldz);
 
 /* Raw Philox4x32-10 blocks (known-answer tests): d_out[4*i..4*i+3] = philox(ctr = d_ctr[4*i..], key). */
 int satmc_philox_blocks(satmc_ctx* ctx, const uint32_t* d_ctr, uint64_t n, uint32_t key0, uint32_t key1,
@@ -156,6 +158,42 @@ int satmc_mc_step(satmc_ctx* ctx, const float* d_robot_base, const float* d_pose
 
 /* count -> probability on a finished tail.   replaces: write_collision_probability utils.cu:210-215 */
 int satmc_write_collision_probability(satmc_ctx* ctx, float* d_counts, int n_done, int n_samples);
+
+/* The whole adaptive-sampling loop of the three programs in one call
+ *   replaces: ztest.cu:328-388, compute_collision_probability.cu:276-333, generate_dataset.cu:420-479
+ *             (while loop: kernel launch, thrust::count, thrust::sort_by_key compaction,
+ *              write_collision_probability on the finished tail, 4-5 blocking D2H copies per iteration)
+ * Tables and per-pair arrays as in satmc_mc_step (n_pairs entries, never permuted).  Every iteration
+ * adds n_batch = (n_samples < switch_at ? n_batch_small : n_batch_large) samples to the unfinished
+ * pairs (generate_dataset.cu:427-431: 1000 / 20000 / 100000; ztest.cu:332: 10000 fixed), evaluates the
+ * z-test stop rule, and retires finished pairs through a device-side work list -- nothing is sorted
+ * and nothing but one int per iteration crosses PCIe.  Stops at max_samples.
+ * d_cp_out[i] = hits_i / samples_i (float division, utils.cu:214), in input order (the reference needs
+ * an index array and a host-side un-permute for that, ztest.cu:390-406).  d_n_samples_out (optional)
+ * receives the samples each pair used.  Pair i always draws Philox stream stream_id_offset + i, so the
+ * result does not depend on the order in which pairs finish. */
+int satmc_adaptive_run(satmc_ctx* ctx, const float* d_robot_base, const float* d_poses, uint32_t n_poses,
+                       const float* d_std_devs, uint32_t n_std, const float* d_pose_idxs,
+                       const float* d_std_dev_idxs, const float* d_positions, int n_pairs,
+                       const float* d_accuracy_bins, const float* d_bin_accuracy, int n_accuracy_bins,
+                       int max_samples, int n_batch_small, int switch_at, int n_batch_large,
+                       uint64_t seed, uint32_t stream_id_offset, float* d_cp_out, int* d_n_samples_out,
+                       int* iterations_out, long long* samples_drawn_out);
+
+/* Iteration-0 draw of generate_dataset: pose index, std-dev index and a robot position on the ring
+ * prior around the obstacle, for n data points.
+ *   replaces: generate_dataset.cu:207-219 (curand() % n, curand_uniform, curand_normal -> Philox) */
+int satmc_sample_positions(satmc_ctx* ctx, const float* d_poses, uint32_t n_poses, const float* d_std_devs,
+                           uint32_t n_std, int n, float r_offset, float spread, uint64_t seed,
+                           uint32_t stream_id_offset, float* d_positions, float* d_pose_idxs,
+                           float* d_std_dev_idxs);
+
+/* Device memory helpers so that host programs need no CUDA headers (cudaMalloc / cudaFree / blocking
+ * cudaMemcpy on the context's device and stream; the reference calls these directly, ztest.cu:269-304). */
+int satmc_device_alloc(satmc_ctx* ctx, void** out, size_t bytes);
+int satmc_device_free(satmc_ctx* ctx, void* p);
+int satmc_upload(satmc_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int satmc_download(satmc_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 
 /* ---- host-buffer convenience (H2D + kernel + D2H inside the call) --------------------------- */
 

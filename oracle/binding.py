@@ -53,7 +53,7 @@ class Oracle:
         L.orc_count_streamed.argtypes = [fp, fp, C.c_size_t, C.c_int, C.c_size_t, u8p]
         L.orc_count_streamed_batch.argtypes = [fp, C.c_size_t, fp, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, u64p, C.c_int]
         L.orc_philox4x32_10.argtypes = [fp, fp, fp]
-        L.orc_fused_normals.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, fp]
+        L.orc_fused_normals.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, fp]
         L.orc_count_fused_batch.argtypes = [fp, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, u64p, C.c_int]
         L.orc_hardware_threads.restype = C.c_int
 
@@ -136,10 +136,10 @@ class Oracle:
         self.lib.orc_philox4x32_10(ctr.ctypes.data, key.ctypes.data, out.ctypes.data)
         return out
 
-    def fused_normals(self, seed, pair_id, index):
+    def fused_normals(self, seed, pair_id, index, ndof=5):
         z = np.zeros(5, np.float32)
-        self.lib.orc_fused_normals(int(seed), int(pair_id), int(index), z.ctypes.data)
-        return z
+        self.lib.orc_fused_normals(int(seed), int(pair_id), int(index), int(ndof), z.ctypes.data)
+        return z[:ndof]
 
     def count_fused_batch(self, pairs, n_samples, seed, sample_offset=0, pair_id_offset=0, threads=0):
         pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)

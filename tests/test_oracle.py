@@ -113,10 +113,14 @@ def test_philox_kat(oracle, ctr, key, out):
 
 
 def test_fused_normals_are_standard_normal(oracle):
-    z = np.array([oracle.fused_normals(123, 7, i) for i in range(20000)])
-    assert np.all(np.abs(z.mean(0)) < 4.5 / math.sqrt(20000))
-    assert np.all(np.abs(z.std(0) - 1) < 0.03)
-    assert np.all(np.abs(np.corrcoef(z.T) - np.eye(5)) < 0.04)
+    for ndof in (3, 5):
+        z = np.array([oracle.fused_normals(123, 7, i, ndof) for i in range(20000)])
+        assert z.shape == (20000, ndof)
+        assert np.all(np.abs(z.mean(0)) < 4.5 / math.sqrt(20000))
+        assert np.all(np.abs(z.std(0) - 1) < 0.03)
+        assert np.all(np.abs(np.corrcoef(z.T) - np.eye(ndof)) < 0.04)
+        # consecutive samples are independent too (they share Philox blocks)
+        assert abs(np.corrcoef(z[:-1, 0], z[1:, ndof - 1])[0, 1]) < 0.04
 
 
 # ---- SAT.py (BASELINE config 1) ---------------------------------------------------------------------

@@ -11,6 +11,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 satmc = importlib.import_module("convex-2d-gpu-collision-detection_b200")
+if os.environ.get("SATMC_LIB"):                 # development only: compare builds of the same source
+    satmc.LIB_PATH = os.environ["SATMC_LIB"]
 wl = importlib.import_module("convex-2d-gpu-collision-detection_b200.workloads")
 
 
@@ -37,12 +39,15 @@ def main():
     ctx = satmc.Context(0, torch.cuda.current_stream().cuda_stream)
     print(torch.cuda.get_device_name(0))
     flags = [0] + ([satmc.SATMC_EXACT_ONLY] if "--exact" in sys.argv else [])
-    for name, pairs, n in (("cfg3 1e5x1e4", wl.dataset_pairs(100_000, 3), 10_000),
+    cases = (("cfg3 1e5x1e4", wl.dataset_pairs(100_000, 3), 10_000),
                            ("cfg3 5dof 1e5x1e4", wl.dataset_pairs(100_000, 3, shape_variance=True), 10_000),
                            ("cfg5 slice 64000x1e5", wl.variance_sweep_pairs(1000, 5), 100_000),
                            ("cfg2 1x1e6", wl.cfg2_pair(), 1_000_000),
                            ("cfg4 slice 1x1e10", wl.cfg2_pair(), 10_000_000_000),
-                           ("ztest 1e5x1000", wl.dataset_pairs(100_000, 3), 1000)):
+                           ("ztest 1e5x1000", wl.dataset_pairs(100_000, 3), 1000))
+    if "--short" in sys.argv:
+        cases = cases[:2] + cases[4:]
+    for name, pairs, n in cases:
         d_pairs = put(pairs); d_hits = torch.zeros(pairs.size, dtype=torch.int64, device="cuda")
         for fl in flags:
             if fl and pairs.size * n > 2e10:
@@ -53,6 +58,8 @@ def main():
             tests = pairs.size * n
             print(f"fused  {name:24s} flags={fl} best {best:9.3f} ms  med {med:9.3f} ms  {tests / best / 1e6:10.2f} Gtests/s "
                   f" exact-eval frac {ev / (tests * (3 + 2 + 7 if pairs.size * n <= 5e9 else 2 + 3)):.2e}  p={d_hits.sum().item() / tests:.4f}")
+    if "--short" in sys.argv and "--streamed" not in sys.argv:
+        return
     # streamed: shared L2-resident bank (cfg5) and HBM-bound private slices
     pairs = wl.variance_sweep_pairs(1000, 5)
     d_pairs = put(pairs); d_hits = torch.zeros(pairs.size, dtype=torch.int64, device="cuda")
