@@ -10,6 +10,7 @@
 // memory, ztest.cu:122-155), which starves the GPU whenever pairs < resident threads.
 #include "../../include/satmc.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdio>
@@ -32,6 +33,13 @@ constexpr int kWarps = kThreads / 32;
 #endif
 #ifndef SATMC_MIN_BLOCKS_STREAMED
 #define SATMC_MIN_BLOCKS_STREAMED 4
+#endif
+// bulk-tensor streamed kernel (measured: 3-DoF 5.58 / 5.73 / 5.26 TB/s, 5-DoF 6.62 / 5.88 / 5.74 TB/s at 2 / 3 / 4 blocks)
+#ifndef SATMC_MIN_BLOCKS_TMA3
+#define SATMC_MIN_BLOCKS_TMA3 3
+#endif
+#ifndef SATMC_MIN_BLOCKS_TMA5
+#define SATMC_MIN_BLOCKS_TMA5 2
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -118,8 +126,8 @@ __device__ __noinline__ unsigned fused_group_slow(const PairConst& P, const floa
 
 // hot path: all four samples of group g
 template <int D>
-__device__ __forceinline__ unsigned fused_group(const PairConst& P, const float* robot, uint64_t g, uint32_t pid,
-                                                const PhiloxKeys& K, unsigned long long* exact_evals)
+__device__ __forceinline__ unsigned fused_group(const PairConst& P, const PairConst& Pcold, const float* robot, uint64_t g,
+                                                uint32_t pid, const PhiloxKeys& K, unsigned long long* exact_evals)
 {
     float n[4 * D];
     group_normals<D>((uint32_t)g, (uint32_t)(g >> 32), pid, K, n);
@@ -133,13 +141,13 @@ __device__ __forceinline__ unsigned fused_group(const PairConst& P, const float*
         cnt += __float_as_uint(m) >> 31;                            // m < 0 (m = -0 / NaN are undecided anyway)
         decided = decided && screen_decided<D>(P, m, hmin);
     }
-    if (!decided) cnt = fused_group_slow<D>(P, robot, g, 0xFu, pid, K, exact_evals);   // rare: redo the group
+    if (!decided) cnt = fused_group_slow<D>(Pcold, robot, g, 0xFu, pid, K, exact_evals);   // rare: redo the group
     return cnt;
 }
 
 // one sample of the streamed path (normals supplied)
 template <int NDOF>
-__device__ __forceinline__ unsigned streamed_sample(const PairConst& P, const float* robot, float z0, float z1,
+__device__ __noinline__ unsigned streamed_sample(const PairConst& P, const float* robot, float z0, float z1,
                                                     float z2, float z3, float z4, unsigned long long* exact_evals)
 {
     float hmin;
@@ -158,9 +166,11 @@ __device__ __forceinline__ unsigned streamed_sample(const PairConst& P, const fl
 
 // samples [b, e) (absolute indices) of one pair: full groups go through the hot loop, the at most two
 // ragged groups at the ends through the slow path on lanes 0 and 1
+// P lives in registers for the hot loop; Pcold is the same data in shared memory, handed to the out-of-line
+// cold functions so that P's address is never taken (otherwise the compiler homes P on the local stack).
 template <int D>
-__device__ __forceinline__ unsigned fused_chunk(const PairConst& P, const float* robot, uint64_t b, uint64_t e,
-                                                uint32_t pid, const PhiloxKeys& K, int lane,
+__device__ __forceinline__ unsigned fused_chunk(const PairConst& P, const PairConst& Pcold, const float* robot, uint64_t b,
+                                                uint64_t e, uint32_t pid, const PhiloxKeys& K, int lane,
                                                 unsigned long long* exact_evals)
 {
     unsigned cnt = 0;
@@ -168,41 +178,91 @@ __device__ __forceinline__ unsigned fused_chunk(const PairConst& P, const float*
     if (g_hi < g_lo) {                                              // whole range inside one group
         if (lane == 0) {
             const unsigned mask = (0xFu << (unsigned)(b & 3)) & (0xFu >> (4 - (unsigned)(e & 3))) & 0xFu;
-            cnt = fused_group_slow<D>(P, robot, b >> 2, mask, pid, K, exact_evals);
+            cnt = fused_group_slow<D>(Pcold, robot, b >> 2, mask, pid, K, exact_evals);
         }
         return cnt;
     }
     for (uint64_t g = g_lo + (uint64_t)lane; g < g_hi; g += 32)
-        cnt += fused_group<D>(P, robot, g, pid, K, exact_evals);
+        cnt += fused_group<D>(P, Pcold, robot, g, pid, K, exact_evals);
     if (lane == 0 && (b & 3))
-        cnt += fused_group_slow<D>(P, robot, b >> 2, (0xFu << (unsigned)(b & 3)) & 0xFu, pid, K, exact_evals);
+        cnt += fused_group_slow<D>(Pcold, robot, b >> 2, (0xFu << (unsigned)(b & 3)) & 0xFu, pid, K, exact_evals);
     if (lane == 1 && (e & 3))
-        cnt += fused_group_slow<D>(P, robot, g_hi, 0xFu >> (4 - (unsigned)(e & 3)), pid, K, exact_evals);
+        cnt += fused_group_slow<D>(Pcold, robot, g_hi, 0xFu >> (4 - (unsigned)(e & 3)), pid, K, exact_evals);
+    return cnt;
+}
+
+// screening value of one streamed sample and whether it is decided (|z| guard included)
+template <int NDOF>
+__device__ __forceinline__ bool streamed_screen(const PairConst& P, float z0, float z1, float z2, float z3, float z4,
+                                                unsigned& hit)
+{
+    float hmin;
+    const float m = screen_gap<NDOF>(P, z0, z1, z2, z3, z4, hmin);
+    hit = __float_as_uint(m) >> 31;
+    bool ok = screen_decided<NDOF>(P, m, hmin);
+    ok = ok & (fabsf(z0) <= SATMC_Z_BOUND) & (fabsf(z1) <= SATMC_Z_BOUND) & (fabsf(z2) <= SATMC_Z_BOUND);
+    if (NDOF == 5) ok = ok & (fabsf(z3) <= SATMC_Z_BOUND) & (fabsf(z4) <= SATMC_Z_BOUND);
+    return ok;
+}
+
+// Cold path of the vector loop: re-read the four samples starting at z[i] (they are still in L1/L2) and decide
+// each with screening + exact fallback; the hot loop keeps nothing alive for it.
+template <int NDOF>
+__device__ __noinline__ unsigned streamed_quad_slow(const PairConst& P, const float* robot, const float* __restrict__ z,
+                                                    uint64_t ldz, uint64_t i, unsigned long long* exact_evals)
+{
+    unsigned cnt = 0;
+    for (int t = 0; t < 4; t++) {
+        const float z0 = z[i + t], z1 = z[ldz + i + t], z2 = z[2 * ldz + i + t];
+        const float z3 = (NDOF == 5) ? z[3 * ldz + i + t] : 0.0f, z4 = (NDOF == 5) ? z[4 * ldz + i + t] : 0.0f;
+        cnt += streamed_sample<NDOF>(P, robot, z0, z1, z2, z3, z4, exact_evals);
+    }
     return cnt;
 }
 
 template <int NDOF>
-__device__ __forceinline__ unsigned streamed_chunk(const PairConst& P, const float* robot, const float* __restrict__ z,
-                                                   uint64_t ldz, uint64_t len, int vec_ok, int lane,
-                                                   unsigned long long* exact_evals)
+struct ZQuad { float4 a, b, c, d, e; };
+
+template <int NDOF>
+__device__ __forceinline__ void load_quad(ZQuad<NDOF>& q, const float* __restrict__ z, uint64_t ldz, uint64_t v)
+{
+    q.a = __ldg(reinterpret_cast<const float4*>(z) + v);
+    q.b = __ldg(reinterpret_cast<const float4*>(z + ldz) + v);
+    q.c = __ldg(reinterpret_cast<const float4*>(z + 2 * ldz) + v);
+    if (NDOF == 5) {
+        q.d = __ldg(reinterpret_cast<const float4*>(z + 3 * ldz) + v);
+        q.e = __ldg(reinterpret_cast<const float4*>(z + 4 * ldz) + v);
+    } else {
+        q.d = make_float4(0.f, 0.f, 0.f, 0.f); q.e = q.d;
+    }
+}
+
+template <int NDOF>
+__device__ __forceinline__ unsigned streamed_chunk(const PairConst& P, const PairConst& Pcold, const float* robot,
+                                                   const float* __restrict__ z, uint64_t ldz, uint64_t len, int vec_ok,
+                                                   int lane, unsigned long long* exact_evals)
 {
     unsigned cnt = 0;
     uint64_t done = 0;
     if (vec_ok) {
+        // 4 samples per lane per trip from one LDG.128 per plane; the next trip's loads are issued before this
+        // trip's arithmetic (register double buffering) so that each warp keeps 2 x ndof x 512 B in flight
         const uint64_t nvec = len / 4;
-        for (uint64_t v = (uint64_t)lane; v < nvec; v += 32) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(z) + v);
-            const float4 b = __ldg(reinterpret_cast<const float4*>(z + ldz) + v);
-            const float4 c = __ldg(reinterpret_cast<const float4*>(z + 2 * ldz) + v);
-            float4 d = make_float4(0.f, 0.f, 0.f, 0.f), e = d;
-            if (NDOF == 5) {
-                d = __ldg(reinterpret_cast<const float4*>(z + 3 * ldz) + v);
-                e = __ldg(reinterpret_cast<const float4*>(z + 4 * ldz) + v);
-            }
-            cnt += streamed_sample<NDOF>(P, robot, a.x, b.x, c.x, d.x, e.x, exact_evals);
-            cnt += streamed_sample<NDOF>(P, robot, a.y, b.y, c.y, d.y, e.y, exact_evals);
-            cnt += streamed_sample<NDOF>(P, robot, a.z, b.z, c.z, d.z, e.z, exact_evals);
-            cnt += streamed_sample<NDOF>(P, robot, a.w, b.w, c.w, d.w, e.w, exact_evals);
+        uint64_t v = (uint64_t)lane;
+        ZQuad<NDOF> cur, nxt;
+        if (v < nvec) load_quad<NDOF>(cur, z, ldz, v);
+        for (; v < nvec; v += 32) {
+            const uint64_t vn = v + 32;
+            if (vn < nvec) load_quad<NDOF>(nxt, z, ldz, vn);
+            unsigned h0, h1, h2, h3;
+            bool ok = streamed_screen<NDOF>(P, cur.a.x, cur.b.x, cur.c.x, cur.d.x, cur.e.x, h0);
+            ok = ok & streamed_screen<NDOF>(P, cur.a.y, cur.b.y, cur.c.y, cur.d.y, cur.e.y, h1);
+            ok = ok & streamed_screen<NDOF>(P, cur.a.z, cur.b.z, cur.c.z, cur.d.z, cur.e.z, h2);
+            ok = ok & streamed_screen<NDOF>(P, cur.a.w, cur.b.w, cur.c.w, cur.d.w, cur.e.w, h3);
+            unsigned c4 = h0 + h1 + h2 + h3;
+            if (!ok) c4 = streamed_quad_slow<NDOF>(Pcold, robot, z, ldz, 4 * v, exact_evals);   // rare: redo the four
+            cnt += c4;
+            cur = nxt;
         }
         done = nvec * 4;
     }
@@ -210,7 +270,7 @@ __device__ __forceinline__ unsigned streamed_chunk(const PairConst& P, const flo
         const float z0 = __ldg(z + i), z1 = __ldg(z + ldz + i), z2 = __ldg(z + 2 * ldz + i);
         float z3 = 0.f, z4 = 0.f;
         if (NDOF == 5) { z3 = __ldg(z + 3 * ldz + i); z4 = __ldg(z + 4 * ldz + i); }
-        cnt += streamed_sample<NDOF>(P, robot, z0, z1, z2, z3, z4, exact_evals);
+        cnt += streamed_sample<NDOF>(Pcold, robot, z0, z1, z2, z3, z4, exact_evals);
     }
     return cnt;
 }
@@ -219,6 +279,7 @@ template <class Src, bool STREAMED>
 __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED : SATMC_MIN_BLOCKS_FUSED) k_count(const __grid_constant__ Src src, const __grid_constant__ CountParams p)
 {
     __shared__ float s_robot[kWarps][8];
+    __shared__ PairConst s_pair[kWarps];
     __shared__ unsigned s_part[kWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t stride = (uint64_t)gridDim.x * kWarps;
@@ -233,22 +294,23 @@ __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED
         pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
         if (p.flags & SATMC_EXACT_ONLY) { P.eps = CUDART_INF_F; P.eps_b = CUDART_INF_F; }
         __syncwarp();
-        if (lane == 0) exact_robot_corners(v[0], v[1], v[2], v[3], v[4], s_robot[warp]);
+        if (lane == 0) { exact_robot_corners(v[0], v[1], v[2], v[3], v[4], s_robot[warp]); s_pair[warp] = P; }
         __syncwarp();
+        const PairConst& Pc = s_pair[warp];
         const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
         const uint64_t c_len = (c_begin + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - c_begin);
         unsigned long long* ev = (p.flags & SATMC_EXACT_ONLY) ? nullptr : p.exact_evals;
         unsigned cnt;
         if (STREAMED) {
             const float* z = p.z + pair * p.z_pair_stride + c_begin;
-            cnt = (p.ndof == 5) ? streamed_chunk<5>(P, s_robot[warp], z, p.ldz, c_len, p.vec_ok, lane, ev)
-                                : streamed_chunk<3>(P, s_robot[warp], z, p.ldz, c_len, p.vec_ok, lane, ev);
+            cnt = (p.ndof == 5) ? streamed_chunk<5>(P, Pc, s_robot[warp], z, p.ldz, c_len, p.vec_ok, lane, ev)
+                                : streamed_chunk<3>(P, Pc, s_robot[warp], z, p.ldz, c_len, p.vec_ok, lane, ev);
         } else {
             const uint32_t pid = p.pair_id_offset + (uint32_t)elem;
             const uint64_t s_begin = p.sample_offset + c_begin;
             const bool dof3 = (v[10] == 0.0f) && (v[11] == 0.0f);
-            cnt = dof3 ? fused_chunk<3>(P, s_robot[warp], s_begin, s_begin + c_len, pid, p.keys, lane, ev)
-                       : fused_chunk<5>(P, s_robot[warp], s_begin, s_begin + c_len, pid, p.keys, lane, ev);
+            cnt = dof3 ? fused_chunk<3>(P, Pc, s_robot[warp], s_begin, s_begin + c_len, pid, p.keys, lane, ev)
+                       : fused_chunk<5>(P, Pc, s_robot[warp], s_begin, s_begin + c_len, pid, p.keys, lane, ev);
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (p.block_uniform) {
@@ -259,6 +321,138 @@ __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED
 #pragma unroll
                 for (int w = 0; w < kWarps; w++) t += s_part[w];
                 atomicAdd(p.hits + pair, t);                       // one atomic per block
+            }
+            __syncthreads();
+        } else if (lane == 0) {
+            if (p.n_chunks == 1) {
+                if (p.flags & SATMC_ACCUMULATE) p.hits[pair] += cnt; else p.hits[pair] = cnt;
+            } else {
+                atomicAdd(p.hits + pair, (unsigned long long)cnt);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// streamed path, bulk-copy staged (the default when the sample bank is 16-byte aligned)
+//
+// The sample bank is described to the TMA unit as a 2-D tensor [ndof planes][ldz samples].  Each warp runs a
+// private 2-stage ring in shared memory: lane 0 issues ONE cp.async.bulk.tensor.2d (UTMALDG) for the next
+// tile of 128 samples x ndof planes, completion is signalled on an mbarrier with expect_tx, and the 32
+// lanes read their 4 samples per plane with one conflict-free LDS.128.  The bytes in flight live in shared
+// memory instead of registers (32 warps x 2 stages x ndof x 512 B per SM) and the hot loop has no LDG and
+// no address arithmetic.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTile = 128;            // samples per tile per plane = 32 lanes x float4
+constexpr int kStages = 2;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" :: "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(smem_addr(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_addr(bar)) : "memory");
+}
+
+template <int NDOF>
+__global__ void __launch_bounds__(kThreads, NDOF == 5 ? SATMC_MIN_BLOCKS_TMA5 : SATMC_MIN_BLOCKS_TMA3)
+k_count_streamed_tma(const __grid_constant__ DirectSrc src, const __grid_constant__ CountParams p,
+                     const __grid_constant__ CUtensorMap zmap)
+{
+    extern __shared__ __align__(128) float s_tiles[];                 // [kWarps][kStages][NDOF][kTile]
+    __shared__ __align__(8) uint64_t s_bar[kWarps][kStages];
+    __shared__ float s_robot[kWarps][8];
+    __shared__ PairConst s_pair[kWarps];
+    __shared__ unsigned s_part[kWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* my_tiles = s_tiles + (size_t)warp * kStages * NDOF * kTile;
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < kStages; st++) mbar_init(&s_bar[warp][st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t tiles_done = 0;                                          // running tile counter: stage and parity
+    const uint64_t stride = (uint64_t)gridDim.x * kWarps;
+    for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < p.n_items; item += stride) {
+        const uint64_t pair = item / p.n_chunks;
+        const uint32_t chunk_id = (uint32_t)(item - pair * p.n_chunks);
+        float v[12];
+        src.load(pair, v);
+        PairConst P;
+        pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
+        if (p.flags & SATMC_EXACT_ONLY) { P.eps = CUDART_INF_F; P.eps_b = CUDART_INF_F; }
+        __syncwarp();
+        if (lane == 0) { exact_robot_corners(v[0], v[1], v[2], v[3], v[4], s_robot[warp]); s_pair[warp] = P; }
+        __syncwarp();
+        const PairConst& Pc = s_pair[warp];
+        const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
+        const uint64_t c_len = (c_begin + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - c_begin);
+        unsigned long long* ev = (p.flags & SATMC_EXACT_ONLY) ? nullptr : p.exact_evals;
+        const float* z = p.z + pair * p.z_pair_stride + c_begin;
+        const uint32_t n_tiles = (uint32_t)(c_len / kTile);
+        const int x0 = (int)(pair * p.z_pair_stride + c_begin);       // tensor coordinate of the chunk (< 2^31, host-checked)
+        auto issue = [&](uint32_t t) {                                // lane 0 only
+            const uint32_t st = (tiles_done + t) % kStages;
+            mbar_expect_tx(&s_bar[warp][st], NDOF * kTile * 4);
+            tma_load_2d(my_tiles + (size_t)st * NDOF * kTile, &zmap, x0 + (int)(t * kTile), 0, &s_bar[warp][st]);
+        };
+        if (lane == 0)
+            for (uint32_t t = 0; t < n_tiles && t < (uint32_t)kStages; t++) issue(t);
+        unsigned cnt = 0;
+        for (uint32_t t = 0; t < n_tiles; t++) {
+            const uint32_t seq = tiles_done + t, st = seq % kStages;
+            mbar_wait(&s_bar[warp][st], (seq / kStages) & 1u);
+            const float4* tp = reinterpret_cast<const float4*>(my_tiles + (size_t)st * NDOF * kTile) + lane;
+            const float4 a = tp[0], b = tp[kTile / 4], c = tp[2 * (kTile / 4)];
+            float4 d = make_float4(0.f, 0.f, 0.f, 0.f), e = d;
+            if (NDOF == 5) { d = tp[3 * (kTile / 4)]; e = tp[4 * (kTile / 4)]; }
+            __syncwarp();                                             // every lane has its samples: the stage is free
+            if (lane == 0 && t + kStages < n_tiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(t + kStages);
+            }
+            unsigned h0, h1, h2, h3;
+            bool ok = streamed_screen<NDOF>(P, a.x, b.x, c.x, d.x, e.x, h0);
+            ok = ok & streamed_screen<NDOF>(P, a.y, b.y, c.y, d.y, e.y, h1);
+            ok = ok & streamed_screen<NDOF>(P, a.z, b.z, c.z, d.z, e.z, h2);
+            ok = ok & streamed_screen<NDOF>(P, a.w, b.w, c.w, d.w, e.w, h3);
+            unsigned c4 = h0 + h1 + h2 + h3;
+            if (!ok) c4 = streamed_quad_slow<NDOF>(Pc, s_robot[warp], z, p.ldz, (uint64_t)t * kTile + 4 * lane, ev);
+            cnt += c4;
+        }
+        tiles_done += n_tiles;
+        for (uint64_t i = (uint64_t)n_tiles * kTile + (uint64_t)lane; i < c_len; i += 32) {      // ragged tail
+            const float z0 = __ldg(z + i), z1 = __ldg(z + p.ldz + i), z2 = __ldg(z + 2 * p.ldz + i);
+            float z3 = 0.f, z4 = 0.f;
+            if (NDOF == 5) { z3 = __ldg(z + 3 * p.ldz + i); z4 = __ldg(z + 4 * p.ldz + i); }
+            cnt += streamed_sample<NDOF>(Pc, s_robot[warp], z0, z1, z2, z3, z4, ev);
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (p.block_uniform) {
+            if (lane == 0) s_part[warp] = cnt;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long tsum = 0;
+#pragma unroll
+                for (int w = 0; w < kWarps; w++) tsum += s_part[w];
+                atomicAdd(p.hits + pair, tsum);
             }
             __syncthreads();
         } else if (lane == 0) {
@@ -450,6 +644,7 @@ struct satmc_ctx {
     int sm_count = 0;
     int blocks_per_sm = 0;
     int blocks_per_sm_streamed = 0;
+    int blocks_per_sm_tma[2] = {0, 0};       // bulk-copy staged streamed kernel, ndof 3 / 5
     char err[512] = {0};
     uint64_t launches = 0;
     unsigned long long* d_exact_evals = nullptr;
@@ -463,6 +658,42 @@ struct satmc_ctx {
 };
 
 static thread_local char g_err[512] = {0};
+
+static inline size_t tma_smem_bytes(int ndof) { return (size_t)kWarps * kStages * ndof * kTile * sizeof(float); }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*tensor_map_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static tensor_map_encode_fn get_tensor_map_encode()
+{
+    static tensor_map_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<tensor_map_encode_fn>(f);
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+// 2-D tensor [ndof][ldz] of float32 over the sample bank, box = [ndof][kTile]
+static bool make_z_tensor_map(CUtensorMap* map, const float* z, uint64_t ldz, int ndof)
+{
+    tensor_map_encode_fn enc = get_tensor_map_encode();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)ldz, (cuuint64_t)ndof};
+    const cuuint64_t strides[1] = {(cuuint64_t)ldz * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kTile, (cuuint32_t)ndof};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(z), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 static int fail(satmc_ctx* ctx, int code, const char* fmt, ...)
 {
@@ -535,6 +766,11 @@ int satmc_create(int device, void* stream, satmc_ctx** out)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_count<DirectSrc, true>, kThreads, 0);
     if (e != cudaSuccess || bps < 1) bps = SATMC_MIN_BLOCKS_STREAMED;
     ctx->blocks_per_sm_streamed = bps;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_count_streamed_tma<3>, kThreads, tma_smem_bytes(3));
+    ctx->blocks_per_sm_tma[0] = (e == cudaSuccess && bps >= 1) ? bps : 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_count_streamed_tma<5>, kThreads, tma_smem_bytes(5));
+    ctx->blocks_per_sm_tma[1] = (e == cudaSuccess && bps >= 1) ? bps : 1;
+    cudaGetLastError();
     if (cudaMalloc(&ctx->d_exact_evals, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(ctx->d_exact_evals, 0, sizeof(unsigned long long)) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
@@ -610,7 +846,11 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
             CU(ctx, cudaMemsetAsync(p.hits, 0, p.n_pairs * sizeof(unsigned long long), ctx->stream));
         return SATMC_OK;
     }
-    const int bps = STREAMED ? ctx->blocks_per_sm_streamed : ctx->blocks_per_sm;
+    // bulk-tensor path: aligned bank, coordinates that fit the TMA's 32-bit signed indices, a driver that encodes the map
+    CUtensorMap zmap;
+    bool tma = STREAMED && p.vec_ok && p.ldz < (1ull << 31) && p.ldz >= (uint64_t)kTile;
+    if (tma) tma = make_z_tensor_map(&zmap, p.z, p.ldz, p.ndof);
+    const int bps = tma ? ctx->blocks_per_sm_tma[p.ndof == 5] : (STREAMED ? ctx->blocks_per_sm_streamed : ctx->blocks_per_sm);
     const uint64_t resident_warps = (uint64_t)ctx->sm_count * bps * kWarps;
     const uint64_t target_items = resident_warps * 8;             // >= 8 items per resident warp when possible
     const uint64_t min_chunk = 2048;                              // 64 samples per lane: amortises the pair prologue
@@ -636,7 +876,16 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
     const uint64_t max_blocks = (uint64_t)ctx->sm_count * bps;
     if (blocks > max_blocks) blocks = max_blocks;
     if (time_it) CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    k_count<Src, STREAMED><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
+    if constexpr (STREAMED) {
+        if (tma && p.ndof == 5)
+            k_count_streamed_tma<5><<<(unsigned)blocks, kThreads, tma_smem_bytes(5), ctx->stream>>>(src, p, zmap);
+        else if (tma)
+            k_count_streamed_tma<3><<<(unsigned)blocks, kThreads, tma_smem_bytes(3), ctx->stream>>>(src, p, zmap);
+        else
+            k_count<Src, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
+    } else {
+        k_count<Src, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
+    }
     CU(ctx, cudaGetLastError());
     if (time_it) { CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream)); ctx->last_ms_valid = true; }
     ctx->launches++;

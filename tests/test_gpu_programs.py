@@ -18,6 +18,16 @@ def programs():
     return {n: os.path.join(HOST, n) for n in ("generate_dataset", "ztest", "compute_collision_probability")}
 
 
+def slack_int64_safe(oracle, n, k):
+    """calcSlack (utils.cu:186-196) with k*k formed exactly: identical to the reference (and the oracle) while
+    k <= 46340; above that the reference's int32 product wraps, which the library does
+    not replicate."""
+    if k == n or k == 0 or k <= 46340:
+        return oracle.calc_slack(n, k)
+    f = np.float32
+    return float(f(1.96) / f(n) * np.sqrt(f(k) - f(k * k) / f(n)))
+
+
 def test_adaptive_run_matches_stepwise_emulation(ctx, dev, oracle, workloads):
     """satmc_adaptive_run == the reference loop semantics (ztest.cu:328-388) emulated pair by pair with
     satmc_count_fused + the oracle's stop rule; results in input order, independent of finishing order."""
@@ -45,7 +55,7 @@ def test_adaptive_run_matches_stepwise_emulation(ctx, dev, oracle, workloads):
         for g in np.nonzero(alive)[0]:
             k = int(total[g])
             p = np.float32(k) / np.float32(n_samples)
-            if oracle.calc_slack(n_samples, k) <= acc[oracle.get_bin(p, bins)]:
+            if slack_int64_safe(oracle, n_samples, k) <= acc[oracle.get_bin(p, bins)]:
                 alive[g] = False; want_cp[g] = np.float32(k) / np.float32(n_samples); want_ns[g] = n_samples
     left = np.nonzero(alive)[0]
     want_cp[left] = total[left].astype(np.float32) / np.float32(n_samples); want_ns[left] = n_samples
