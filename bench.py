@@ -38,9 +38,9 @@ PKG = "convex-2d-gpu-collision-detection_b200"
 METRIC = "SAT pair-tests/sec"
 UNIT = "tests/s"
 # FMA-pipe cost of one test in the fused 3-DoF loop, read off the SASS of k_count:
-# per 4-sample group 160 FP32 (FFMA/FMUL/FADD, 1 slot each) + 60 IMAD.WIDE (quarter rate on sm_100a: 4 slots)
-# + 2 IMAD (2 slots) = 404 FFMA-equivalent issue slots -> 101 per test.
-FMA_SLOTS_PER_TEST = 101.0
+# per 4-sample group 124 FP32 (FFMA/FMUL/FADD, 1 slot each) + 60 IMAD.WIDE (quarter rate on sm_100a: 4 slots)
+# = 364 FFMA-equivalent issue slots -> 91 per test.
+FMA_SLOTS_PER_TEST = 91.0
 SURVEY_I_FMA_W8 = 247.0      # 8-axis kernel, 3-DoF
 SURVEY_I_FMA_W4 = 163.0      # 4-axis kernel (+ exact fallback), 3-DoF
 
@@ -310,11 +310,11 @@ def main():
                 "achieved": per_gpu * FMA_SLOTS_PER_TEST / 1e12, "peak": fma_peak / 1e12, "unit": "T FFMA-equivalent lane-slots/s",
                 "frac": per_gpu * FMA_SLOTS_PER_TEST / fma_peak, "traffic": 4.85e6,
                 "peak_source": f"148 SM x 128 lanes x sm_max_mhz {sm_mhz:.0f} from {src}",
-                "alg_units": "101 FMA-pipe issue slots per test (SASS: per 4-sample group 160 FP32 + 60 IMAD.WIDE x4 + 2 IMAD x2)",
+                "alg_units": "91 FMA-pipe issue slots per test (SASS: per 4-sample group 124 FP32 + 60 IMAD.WIDE x4)",
                 "frac_vs_survey_w8_model": per_gpu * SURVEY_I_FMA_W8 / fma_peak,
                 "frac_vs_survey_w4_model": per_gpu * SURVEY_I_FMA_W4 / fma_peak,
                 "note": "the fractions above 1 are against SURVEY.md section 8(d)'s instruction models (247 / 163 FMA-pipe "
-                        "instructions per test); this kernel needs ~55 (screening pass), so frac is quoted on its own SASS count",
+                        "instructions per test); this kernel needs ~46 (screening pass), so frac is quoted on its own SASS count",
             },
             "hits_checksum": hits_total,
         }

@@ -424,10 +424,7 @@ k_count_streamed_tma(const __grid_constant__ DirectSrc src, const __grid_constan
             float4 d = make_float4(0.f, 0.f, 0.f, 0.f), e = d;
             if (NDOF == 5) { d = tp[3 * (kTile / 4)]; e = tp[4 * (kTile / 4)]; }
             __syncwarp();                                             // every lane has its samples: the stage is free
-            if (lane == 0 && t + kStages < n_tiles) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue(t + kStages);
-            }
+            if (lane == 0 && t + kStages < n_tiles) issue(t + kStages);   // __syncwarp ordered the reads before this write
             unsigned h0, h1, h2, h3;
             bool ok = streamed_screen<NDOF>(P, a.x, b.x, c.x, d.x, e.x, h0);
             ok = ok & streamed_screen<NDOF>(P, a.y, b.y, c.y, d.y, e.y, h1);

@@ -110,11 +110,10 @@ __device__ __forceinline__ int exact_convex_collide(const float r1[8], const flo
 // ---------------------------------------------------------------------------------------------
 struct PairConst {
     // screening pass (robot: centre P, axes A0=(ca,sa), A1=(-sa,ca), half extents a0,a1;
-    //                 obstacle: centre (sd_x z0, sd_y z1), angle sd_t z2, half extents b0,b1)
-    float px, py, nsx, nsy;          // u = P - d :  ux = fma(nsx, z0, px)
-    float pa0, pa1;                  // P.A0, P.A1
-    float nkx0, nky0, kx1, nky1;     // u.A0 = pa0 + nkx0 z0 + nky0 z1 ; u.A1 = pa1 + kx1 z0 + nky1 z1
-    float ca, sa;
+    //                 obstacle: centre d = (sd_x z0, sd_y z1), angle dt = sd_t z2, half extents b0,b1)
+    float pa0, pa1;                  // P.A0, P.A1 (robot centre in the robot's own frame)
+    float nkx0, nky0, kx1, nky1;     // u.A0 = pa0 + nkx0 z0 + nky0 z1 ; u.A1 = pa1 + kx1 z0 + nky1 z1,  u = P - d
+    float th, nst;                   // phi = th + nst*z2 = (robot heading reduced to [-pi,pi]) - sd_t*z2
     float a0, a1, b0, b1;
     float hw, hh;                    // 0.5*sd_w, 0.5*sd_h  (5-DoF half-extent perturbation)
     float eps;                       // 3-DoF screening threshold eps_a + eps_b / min(b0,b1); +inf => always exact
@@ -131,7 +130,7 @@ struct PairConst {
 // The bound has the form eps = eps_a + eps_b / hmin, hmin = the smaller obstacle half extent (the
 // obstacle's edge axes are known to relative accuracy ~ corner error / edge length).  With shape
 // variance hmin changes per sample, so the two parts are kept separate.
-__device__ __forceinline__ void screen_eps(float px, float py, float a0, float a1, float b0, float b1,
+__device__ __forceinline__ void screen_eps(float px, float py, float theta, float a0, float a1, float b0, float b1,
                                            float sd_x, float sd_y, float sd_t, float sd_w, float sd_h,
                                            float& eps_a, float& eps_b)
 {
@@ -147,14 +146,18 @@ __device__ __forceinline__ void screen_eps(float px, float py, float a0, float a
     const float dS = u * (7.0f * r1b + fmaxf(dmx, dmy));
     const float dR = u * (7.0f * r1a + pn);
     const float LA = 2.0f * fminf(a0, a1);
-    const float e_m = 9.5367432e-7f + 4.0f * u * dmt;                 // |__sinf/__cosf - sin/cos|, |x| <= dmt
+    // relative angle phi = theta_r - dt, |phi| <= pi + dmt.  |__sinf/__cosf - sin/cos|(x) <= 2^-20 + 4u|x| (measured on
+    // B200, profiles/r1_trig_err.log); the float phi differs from the real theta - dt by <= 2u(|phi| + dmt + |theta|)
+    // (rounding of the fma, of dt in the exact pass, and of the reduction of theta)
+    const float phimax = 3.1415927f + dmt;
+    const float e_m = 9.5367432e-7f + 4.0f * u * phimax + 2.0f * u * (phimax + dmt + fabsf(theta));
     const float e_fast = (un + 2.0f * (r1a + r1b)) * e_m + 24.0f * u * M;
     const float e_ref_a = 5.5f * u * M + 1.5f * (dS + dR) + 3.0f * M * dR / LA;
     float ea = 1.0625f * (e_ref_a + e_fast);
     float eb = 1.0625f * 1.5f * M * dS;                               // 3 M dS / LB, LB = 2 hmin
     // outside the validated domain of the bound (degenerate robot, huge angles, non-finite or
     // astronomically large input): never trust the screening pass
-    const bool ok = (LA > 0.0f) && (dmt <= 64.0f) && (ea == ea) && (eb == eb) && (M < 1.0e18f);
+    const bool ok = (LA > 0.0f) && (dmt <= 64.0f) && (fabsf(theta) <= 1.0e4f) && (ea == ea) && (eb == eb) && (M < 1.0e18f);
     eps_a = ok ? ea : CUDART_INF_F;
     eps_b = ok ? eb : CUDART_INF_F;
 }
@@ -164,17 +167,18 @@ __device__ __forceinline__ void pair_const_init(PairConst& P, float rx, float ry
                                                 float sd_t, float sd_w, float sd_h)
 {
     const float ca = cosf(rtheta), sa = sinf(rtheta);
-    P.px = rx; P.py = ry; P.nsx = -sd_x; P.nsy = -sd_y;
-    P.ca = ca; P.sa = sa;
     P.pa0 = fmaf(rx, ca, ry * sa);
     P.pa1 = fmaf(ry, ca, -(rx * sa));
     P.nkx0 = -(sd_x * ca); P.nky0 = -(sd_y * sa);
     P.kx1 = sd_x * sa;     P.nky1 = -(sd_y * ca);
+    const float k = rintf(rtheta * 0.15915494f);                     // heading reduced to [-pi, pi] (2 pi = hi + lo)
+    P.th = fmaf(-k, -1.7484555e-7f, fmaf(-k, 6.2831855f, rtheta));
+    P.nst = -sd_t;
     P.a0 = 0.5f * fabsf(rw); P.a1 = 0.5f * fabsf(rh);
     P.b0 = 0.5f * fabsf(ow); P.b1 = 0.5f * fabsf(oh);
     P.hw = 0.5f * sd_w;      P.hh = 0.5f * sd_h;
     P.ow = ow; P.oh = oh; P.sd_x = sd_x; P.sd_y = sd_y; P.sd_t = sd_t; P.sd_w = sd_w; P.sd_h = sd_h;
-    screen_eps(rx, ry, P.a0, P.a1, P.b0, P.b1, sd_x, sd_y, sd_t, sd_w, sd_h, P.eps_a, P.eps_b);
+    screen_eps(rx, ry, rtheta, P.a0, P.a1, P.b0, P.b1, sd_x, sd_y, sd_t, sd_w, sd_h, P.eps_a, P.eps_b);
     const float hmin = fminf(P.b0, P.b1);
     const float e3 = P.eps_a + P.eps_b / hmin;
     P.eps = (hmin > 0.0f && e3 == e3) ? e3 : CUDART_INF_F;
@@ -182,21 +186,22 @@ __device__ __forceinline__ void pair_const_init(PairConst& P, float rx, float ry
 
 // ---------------------------------------------------------------------------------------------
 // screening pass: largest normalised signed gap over the 4 box axes (m > 0 separated, m < 0 overlap)
+// 22 FP32 instructions + 2 MUFU per sample (3-DoF)
 // ---------------------------------------------------------------------------------------------
 template <int NDOF>
 __device__ __forceinline__ float screen_gap(const PairConst& P, float z0, float z1, float z2, float z3, float z4,
                                             float& hmin)
 {
-    const float dt = __fmul_rn(z2, P.sd_t);              // the same float the exact pass feeds to sinf/cosf
-    const float s = __sinf(dt), c = __cosf(dt);
-    const float ux = fmaf(P.nsx, z0, P.px);
-    const float uy = fmaf(P.nsy, z1, P.py);
-    const float ub0 = fmaf(ux, c, uy * s);
-    const float ub1 = fmaf(uy, c, -(ux * s));
+    // u in the robot frame, then rotated by the relative angle phi = theta - dt into the obstacle frame:
+    // u.B0 = cos(phi) u.A0 - sin(phi) u.A1,  u.B1 = sin(phi) u.A0 + cos(phi) u.A1;  |A_i.B_j| = |cos phi|, |sin phi|
+    const float phi = fmaf(P.nst, z2, P.th);
+    const float s = __sinf(phi), c = __cosf(phi);
     const float ua0 = fmaf(P.nkx0, z0, fmaf(P.nky0, z1, P.pa0));
     const float ua1 = fmaf(P.kx1, z0, fmaf(P.nky1, z1, P.pa1));
-    const float C = fabsf(fmaf(P.ca, c, P.sa * s));
-    const float S = fabsf(fmaf(P.sa, c, -(P.ca * s)));
+    const float ub0 = fmaf(c, ua0, -(s * ua1));
+    const float ub1 = fmaf(s, ua0, c * ua1);
+    const float C = fabsf(c);
+    const float S = fabsf(s);
     float hx = P.b0, hy = P.b1;
     // a perturbation past -width flips the corner order but spans the same rectangle: |half extent|
     if (NDOF == 5) { hx = fabsf(fmaf(z3, P.hw, hx)); hy = fabsf(fmaf(z4, P.hh, hy)); }

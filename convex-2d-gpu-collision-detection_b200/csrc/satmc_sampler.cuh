@@ -12,9 +12,8 @@
 //       -> 4 words -> two Box-Muller pairs -> normals n[4j..4j+3] = (cos0, sin0, cos1, sin1)
 //     sample 4g+t uses n[D*t .. D*t+D-1] in the order x, y, theta[, w, h].
 //   Box-Muller on words (a, b):
-//     U     = RN((a + 0.5) * 2^-32)             (float in [2^-33, 1]; exact for small values, so the tail
-//                                                 has 32-bit resolution: largest radius sqrt(2*33*ln2) = 6.76,
-//                                                 cuRAND's is 6.66)
+//     U     = RN(RN(a) * 2^-32 + 2^-33)         (float in [2^-33, 1]; exact for small a, so the tail has 32-bit
+//                                                 resolution: largest radius sqrt(2*33*ln2) = 6.76, cuRAND's 6.66)
 //     R     = sqrt(-2 ln U) = sqrt(-2 ln2 * log2 U)
 //     phi   = 2 pi * ((b & 0x7fffff) + 0.5) * 2^-23
 //     (R cos phi, R sin phi)
@@ -63,17 +62,15 @@ __device__ __forceinline__ float mufu_sqrt(float x) { float y; asm("sqrt.approx.
 __device__ __forceinline__ float mufu_sin(float x)  { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_cos(float x)  { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// radius of the Box-Muller pair from one 32-bit word:  U = (a + 0.5) * 2^-32 in (0,1], R = sqrt(-2 ln U)
+// radius of the Box-Muller pair from one 32-bit word:  U = RN(RN(a) * 2^-32 + 2^-33) in (0,1], R = sqrt(-2 ln U)
 __device__ __forceinline__ float bm_radius(uint32_t a)
 {
-    // (a >> 16) * 2^-16 and (a & 0xffff) * 2^-32 through magic exponents: two PRMTs, no I2F.
-    // U is formed near 1 for small radii, where lg2.approx is accurate to 2^-22 absolute, so the radius
-    // keeps ~1e-7 resolution at R -> 0 (the same resolution as cuRAND's float uniform + logf).
-    const float hf = __uint_as_float(__byte_perm(a, 0x43000000u, 0x7632));   // 128 + (a >> 16) * 2^-16
-    const float lf = __uint_as_float(__byte_perm(a, 0x3b000000u, 0x7610));   // 2^-9 + (a & 0xffff) * 2^-32
-    const float hi = __fadd_rn(hf, -128.0f);                                 // exact
-    const float lo = __fadd_rn(lf, -0.001953124883584678173065185546875f);   // - (2^-9 - 2^-33): (a & 0xffff + 0.5) * 2^-32, exact
-    const float U = __fadd_rn(hi, lo);                                       // RN((a + 0.5) * 2^-32) in [2^-33, 1]
+    // I2FP.F32.U32 runs on the ALU pipe at half rate on sm_100a (tools/ubench.cu), cheaper than assembling the
+    // float from 16-bit halves on the FMA pipe.  Small a convert exactly, so the tail keeps 32-bit resolution
+    // (largest radius sqrt(2*33*ln2) = 6.76; cuRAND's is 6.66); near U = 1 (small radii) the spacing is the
+    // float spacing 2^-24, where lg2.approx is accurate to 2^-22 absolute -- the same resolution as cuRAND's
+    // float uniform + logf.
+    const float U = __fmaf_rn(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
     const float r2 = __fmul_rn(mufu_lg2(U), -1.3862943611198906f);           // -2 ln U >= 0
     return mufu_sqrt(fabsf(r2));
 }

@@ -31,6 +31,11 @@ __global__ void __launch_bounds__(1024, 1) k(uint32_t seed, uint32_t* sink, long
             if (OP == 9) { f[i] = fmaf(f[i], 1.0000001f, 1e-9f); a[i] = a[i] * 0xD2511F53u + seed; }                         // FFMA + IMAD mix
             if (OP == 10) { f[i] = fmaf(f[i], 1.0000001f, 1e-9f); a[i] = (a[i] ^ seed) & (a[(i + 1) % ILP] | 0x55u); }       // FFMA + LOP3 mix
             if (OP == 11) { f[i] = f[i] + 1e-9f; }                                                                          // FADD
+            if (OP == 12) { f[i] = __uint2float_rn(__float_as_uint(f[i]) ^ a[i]); }                                         // I2F.U32 + LOP3
+            if (OP == 13) { a[i] = __umulhi(a[i], 0xD2511F53u) + seed; }                                                    // IMAD.HI
+            if (OP == 14) { uint64_t p = (uint64_t)a[i] * 0xD2511F53u + (uint64_t)a[(i + 1) % ILP]; a[i] = (uint32_t)(p >> 32); }  // IMAD.WIDE with add (chained on hi)
+            if (OP == 15) { asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(f[i])); }                                     // MUFU.SQRT
+            if (OP == 16) { a[i] = __float_as_uint(f[i] = fmaf(f[i], 1.0000001f, 1e-9f)) >> 31; }                           // FFMA + SHF
         }
     }
     long long t1 = clock64();
@@ -60,6 +65,7 @@ template <int OP> void run(const char* name, int instr_per_op)
 int main()
 {
     run<3>("FFMA", 1); run<11>("FADD", 1); run<1>("IMAD", 1); run<0>("IMAD.WIDE+LOP3", 2); run<7>("IMAD.WIDE+IADD3", 2); run<2>("LOP3(x2)", 2);
+    run<12>("I2F.U32+LOP3", 2); run<13>("IMAD.HI", 1); run<14>("IMAD.WIDE(+c)", 1); run<15>("MUFU.SQRT", 1);
     run<5>("PRMT", 1); run<6>("FMNMX+FMUL", 2); run<4>("MUFU.LG2", 1); run<8>("FMUL+MUFU.SIN", 2); run<9>("FFMA+IMAD", 2); run<10>("FFMA+LOP3x2", 3);
     return 0;
 }
