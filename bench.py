@@ -367,11 +367,30 @@ def extras(ctx, mod, wl, torch, hbm_peak, src):
     one = put(wl.cfg2_pair()); d_h1 = torch.zeros(1, dtype=torch.int64, device="cuda")
     ms = timed(lambda: ctx.count_fused(one, 1, 1_000_000, 7, d_h1), reps=20, warm=5)
     out["cfg2_fused_1pair_1e6"] = {"tests_per_s": 1e6 / ms * 1e3, "ms": ms}
+    # the adaptive z-test batch (what generate_dataset / compute_collision_probability do per file)
+    pairs = wl.dataset_pairs(100_000, 3)
+    rb, poses, sds, pi, si, pos = wl.reference_tables(pairs)
+    bins = np.array([0, 0.01, 0.1, 1.0], np.float32); acc = np.array([1e-4, 1e-3, 1e-2], np.float32)
+    max_samples = 1_020_000
+    dd = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (rb, poses.ravel(), sds.ravel(), pi, si, pos.ravel(), bins, acc)]
+    d_cp = torch.zeros(pairs.size, device="cuda")
+
+    def adaptive():
+        return ctx.adaptive_run(dd[0], dd[1], pairs.size, dd[2], pairs.size, dd[3], dd[4], dd[5], pairs.size, dd[6], dd[7], 4,
+                                max_samples, 1000, 20000, 100000, 7, d_cp)
+    adaptive(); torch.cuda.synchronize()
+    t0 = time.perf_counter(); iters, drawn = adaptive(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    out["adaptive_batch"] = {"pairs": int(pairs.size), "max_samples": max_samples, "ms": dt * 1e3, "iterations": iters,
+                             "samples_drawn": drawn, "tests_per_s": drawn / dt, "pair_probabilities_per_s": pairs.size / dt,
+                             "what": "satmc_adaptive_run: schedule 1000/20000/100000, bins 0|0.01|0.1|1, accuracy 1e-4|1e-3|1e-2, wall clock"}
     try:
         from oracle.binding import RefGpu
         ref = RefGpu()
-        pairs = wl.dataset_pairs(100_000, 3)
-        rb, poses, sds, pi, si, pos = wl.reference_tables(pairs)
+        _, ms, drawn_ref = ref.adaptive_batch(rb, poses, sds, pi, si, pos, bins, acc, max_samples, 3)
+        out["reference_adaptive_batch"] = {"ms": ms, "samples_drawn": drawn_ref, "tests_per_s": drawn_ref / ms * 1e3,
+                                           "pair_probabilities_per_s": pairs.size / ms * 1e3,
+                                           "what": "the reference's loop (its kernel + thrust::count + thrust::sort_by_key + tail copies) "
+                                                   "recompiled for sm_100a, same batch and schedule, wall clock"}
         ref.mc_time(rb, poses, sds, pi, si, pos, 1000, 2, 1)
         ms, _ = ref.mc_time(rb, poses, sds, pi, si, pos, 1000, 10, 1)
         out["reference_gpu_kernel_cfg3"] = {"tests_per_s": 1e9 / ms * 1e3, "ms": ms,

@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED
         pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
         if (p.flags & SATMC_EXACT_ONLY) { P.eps = CUDART_INF_F; P.eps_b = CUDART_INF_F; }
         __syncwarp();
-        if (lane == 0) { exact_robot_corners(v[0], v[1], v[2], v[3], v[4], s_robot[warp]); s_pair[warp] = P; }
+        if (lane == 0) { exact_robot_corners(v[0], v[1], P.ca, P.sa, v[3], v[4], s_robot[warp]); s_pair[warp] = P; }
         __syncwarp();
         const PairConst& Pc = s_pair[warp];
         const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
@@ -399,7 +399,7 @@ k_count_streamed_tma(const __grid_constant__ DirectSrc src, const __grid_constan
         pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
         if (p.flags & SATMC_EXACT_ONLY) { P.eps = CUDART_INF_F; P.eps_b = CUDART_INF_F; }
         __syncwarp();
-        if (lane == 0) { exact_robot_corners(v[0], v[1], v[2], v[3], v[4], s_robot[warp]); s_pair[warp] = P; }
+        if (lane == 0) { exact_robot_corners(v[0], v[1], P.ca, P.sa, v[3], v[4], s_robot[warp]); s_pair[warp] = P; }
         __syncwarp();
         const PairConst& Pc = s_pair[warp];
         const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
@@ -475,7 +475,7 @@ __global__ void k_decide(satmc_pair const* pair, const float* __restrict__ z, ui
     PairConst P;
     pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
     if (flags & SATMC_EXACT_ONLY) { P.eps = CUDART_INF_F; P.eps_b = CUDART_INF_F; }
-    if (threadIdx.x == 0) exact_robot_corners(v[0], v[1], v[2], v[3], v[4], s_robot);
+    if (threadIdx.x == 0) exact_robot_corners(v[0], v[1], P.ca, P.sa, v[3], v[4], s_robot);
     __syncthreads();
     unsigned long long* ev = (flags & SATMC_EXACT_ONLY) ? nullptr : exact_evals;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {

@@ -33,11 +33,11 @@ namespace satmc {
 
 // create_rect(w,h) [utils.cu:119-130] + rot_trans_rectangle(pos, theta) [utils.cu:132-142] for the
 // robot (ztest.cu:148-149,297):  x' = FADD(FFMA(x,c,-FMUL(y,s)), px)   y' = FADD(FFMA(x,s,FMUL(y,c)), py)
-__device__ __forceinline__ void exact_robot_corners(float px, float py, float theta, float rw, float rh,
+__device__ __forceinline__ void exact_robot_corners(float px, float py, float c, float s, float rw, float rh,
                                                     float r[8])
 {
+    // c, s = cosf(pose.theta), sinf(pose.theta): the precise libdevice values (PairConst::ca, sa)
     const float hx = rw / 2, hy = rh / 2;
-    const float c = cosf(theta), s = sinf(theta);
     const float bx[4] = {-hx, hx, hx, -hx};
     const float by[4] = {-hy, -hy, hy, hy};
 #pragma unroll
@@ -111,6 +111,7 @@ __device__ __forceinline__ int exact_convex_collide(const float r1[8], const flo
 struct PairConst {
     // screening pass (robot: centre P, axes A0=(ca,sa), A1=(-sa,ca), half extents a0,a1;
     //                 obstacle: centre d = (sd_x z0, sd_y z1), angle dt = sd_t z2, half extents b0,b1)
+    float ca, sa;                    // cosf/sinf(robot heading), precise (also used for the exact robot corners)
     float pa0, pa1;                  // P.A0, P.A1 (robot centre in the robot's own frame)
     float nkx0, nky0, kx1, nky1;     // u.A0 = pa0 + nkx0 z0 + nky0 z1 ; u.A1 = pa1 + kx1 z0 + nky1 z1,  u = P - d
     float th, nst;                   // phi = th + nst*z2 = (robot heading reduced to [-pi,pi]) - sd_t*z2
@@ -152,7 +153,7 @@ __device__ __forceinline__ void screen_eps(float px, float py, float theta, floa
     const float phimax = 3.1415927f + dmt;
     const float e_m = 9.5367432e-7f + 4.0f * u * phimax + 2.0f * u * (phimax + dmt + fabsf(theta));
     const float e_fast = (un + 2.0f * (r1a + r1b)) * e_m + 24.0f * u * M;
-    const float e_ref_a = 5.5f * u * M + 1.5f * (dS + dR) + 3.0f * M * dR / LA;
+    const float e_ref_a = 5.5f * u * M + 1.5f * (dS + dR) + 3.0f * M * __fdividef(dR, LA);   // 2-ulp division: inside the 6 % slack
     float ea = 1.0625f * (e_ref_a + e_fast);
     float eb = 1.0625f * 1.5f * M * dS;                               // 3 M dS / LB, LB = 2 hmin
     // outside the validated domain of the bound (degenerate robot, huge angles, non-finite or
@@ -167,6 +168,7 @@ __device__ __forceinline__ void pair_const_init(PairConst& P, float rx, float ry
                                                 float sd_t, float sd_w, float sd_h)
 {
     const float ca = cosf(rtheta), sa = sinf(rtheta);
+    P.ca = ca; P.sa = sa;
     P.pa0 = fmaf(rx, ca, ry * sa);
     P.pa1 = fmaf(ry, ca, -(rx * sa));
     P.nkx0 = -(sd_x * ca); P.nky0 = -(sd_y * sa);
@@ -180,7 +182,7 @@ __device__ __forceinline__ void pair_const_init(PairConst& P, float rx, float ry
     P.ow = ow; P.oh = oh; P.sd_x = sd_x; P.sd_y = sd_y; P.sd_t = sd_t; P.sd_w = sd_w; P.sd_h = sd_h;
     screen_eps(rx, ry, rtheta, P.a0, P.a1, P.b0, P.b1, sd_x, sd_y, sd_t, sd_w, sd_h, P.eps_a, P.eps_b);
     const float hmin = fminf(P.b0, P.b1);
-    const float e3 = P.eps_a + P.eps_b / hmin;
+    const float e3 = P.eps_a + __fdividef(P.eps_b, hmin);
     P.eps = (hmin > 0.0f && e3 == e3) ? e3 : CUDART_INF_F;
 }
 

@@ -166,6 +166,7 @@ class RefGpu:
         L.ref_dev_sincos.argtypes = [vp, C.c_int, vp, vp, C.c_int]
         L.ref_fast_trig_err.argtypes = [C.c_float, C.c_float, vp, vp]
         L.ref_mc_time.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+        L.ref_adaptive_batch.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp]
 
     @staticmethod
     def _ok(rc):
@@ -223,6 +224,19 @@ class RefGpu:
         c = _f32(counts).copy()
         self._ok(self.lib.ref_write_cp(c.ctypes.data, c.size, n_samples))
         return c
+
+    def adaptive_batch(self, robot_base, poses, std_devs, pose_idxs, sd_idxs, positions, bins, bin_acc, max_samples, seed):
+        """The reference's whole adaptive loop (its kernel + thrust compaction). Returns (cp in input order, ms, samples drawn)."""
+        robot_base, poses, std_devs = _f32(robot_base), _f32(poses).reshape(-1, 3), _f32(std_devs).reshape(-1, 5)
+        pose_idxs, sd_idxs, positions = _f32(pose_idxs), _f32(sd_idxs), _f32(positions).reshape(-1, 2)
+        bins, bin_acc = _f32(bins), _f32(bin_acc)
+        n = positions.shape[0]
+        cp = np.zeros(n, np.float32); ms = C.c_float(0); drawn = C.c_longlong(0)
+        self._ok(self.lib.ref_adaptive_batch(robot_base.ctypes.data, poses.ctypes.data, poses.shape[0], std_devs.ctypes.data,
+                                             std_devs.shape[0], pose_idxs.ctypes.data, sd_idxs.ctypes.data, positions.ctypes.data, n,
+                                             bins.ctypes.data, bins.size, bin_acc.ctypes.data, int(max_samples), int(seed),
+                                             cp.ctypes.data, C.byref(ms), C.byref(drawn)))
+        return cp, float(ms.value), int(drawn.value)
 
     def mc_time(self, robot_base, poses, std_devs, pose_idxs, sd_idxs, positions, n_batch, launches, seed):
         robot_base, poses, std_devs = _f32(robot_base), _f32(poses).reshape(-1, 3), _f32(std_devs).reshape(-1, 5)

@@ -17,12 +17,15 @@
 //                           kernel is about to draw so another implementation can consume the same ones)
 //   ref_write_cp         -> write_collision_probability  utils.cu:210-215
 //   ref_mc_time          -> the reference kernel timed with CUDA events (reference-GPU baseline)
+//   ref_adaptive_batch   -> the reference's adaptive loop (kernel + thrust::count + thrust::sort_by_key + tail copies)
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 #include <string>
 #include <numeric>
 #include <cstring>
+#include <chrono>
+#include <cmath>
 
 #define main ztest_reference_main
 #include "ztest.cu"
@@ -277,6 +280,80 @@ int ref_mc_time(const float* robot_base, const float* poses, int n_poses, const 
     RG_CHECK(cudaEventElapsedTime(ms_out, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (cps_out) RG_CHECK(cudaMemcpy(cps_out, d_cp.p, (size_t)num_left * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// The reference's adaptive loop around its own kernel, as compute_collision_probability.cu:276-333 /
+// generate_dataset.cu:420-479 run it (schedule 1000 -> 100000 at 20000 samples, thrust::count, stable
+// thrust::sort_by_key compaction over a zip of (position, cp, var_idx, pose_idx, index),
+// write_collision_probability on the finished tail, blocking D2H copies of the tail), timed end to end with a
+// host clock.  The loop body is re-typed here because the reference's main() also does file I/O and needs boost;
+// the kernel, the thrust calls and their order are the reference's.  Returns probabilities in input order.
+int ref_adaptive_batch(const float* robot_base, const float* poses, int n_poses, const float* std_devs, int n_sd,
+                       const float* pose_idxs, const float* sd_idxs, const float* positions, int n,
+                       const float* accuracy_bins, int n_bins, const float* bin_accuracy, int max_samples, int seed,
+                       float* cp_out, float* ms_out, long long* samples_out) {
+    int padded = ((n + THREADS - 1) / THREADS) * THREADS;
+    DevBuf<float> d_robot, d_pi, d_si, d_cp, d_bins, d_acc;
+    DevBuf<Pose> d_poses; DevBuf<StdDev> d_sd; DevBuf<Position> d_pos; DevBuf<int> d_done, d_index;
+    DevBuf<curandState> st;
+    RG_CHECK(d_robot.alloc(8)); RG_CHECK(d_poses.alloc(n_poses)); RG_CHECK(d_sd.alloc(n_sd));
+    RG_CHECK(d_pi.alloc(n)); RG_CHECK(d_si.alloc(n)); RG_CHECK(d_pos.alloc(n)); RG_CHECK(d_cp.alloc(n));
+    RG_CHECK(d_done.alloc(n)); RG_CHECK(d_index.alloc(n)); RG_CHECK(d_bins.alloc(n_bins + 1)); RG_CHECK(d_acc.alloc(n_bins + 1));
+    RG_CHECK(st.alloc(padded));
+    RG_CHECK(cudaMemset(d_bins.p, 0, (n_bins + 1) * sizeof(float))); RG_CHECK(cudaMemset(d_acc.p, 0, (n_bins + 1) * sizeof(float)));
+    RG_CHECK(cudaMemset(d_cp.p, 0, (size_t)n * sizeof(float)));
+    std::vector<int> index(n); std::iota(index.begin(), index.end(), 0);
+    std::vector<float> cp(n), vi(n), pi(n); std::vector<Position> pos(n);
+    RG_CHECK(cudaMemcpy(d_robot.p, robot_base, 8 * sizeof(float), cudaMemcpyHostToDevice));
+    RG_CHECK(cudaMemcpy(d_poses.p, poses, (size_t)n_poses * sizeof(Pose), cudaMemcpyHostToDevice));
+    RG_CHECK(cudaMemcpy(d_sd.p, std_devs, (size_t)n_sd * sizeof(StdDev), cudaMemcpyHostToDevice));
+    RG_CHECK(cudaMemcpy(d_bins.p, accuracy_bins, (size_t)n_bins * sizeof(float), cudaMemcpyHostToDevice));
+    RG_CHECK(cudaMemcpy(d_acc.p, bin_accuracy, (size_t)(n_bins - 1) * sizeof(float), cudaMemcpyHostToDevice));
+    setup_kernel<<<padded / THREADS, THREADS>>>(st.p, seed);
+    RG_CHECK(cudaDeviceSynchronize());
+    auto t0 = std::chrono::steady_clock::now();
+    RG_CHECK(cudaMemcpy(d_index.p, index.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    RG_CHECK(cudaMemcpy(d_pos.p, positions, (size_t)n * sizeof(Position), cudaMemcpyHostToDevice));
+    RG_CHECK(cudaMemcpy(d_pi.p, pose_idxs, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    RG_CHECK(cudaMemcpy(d_si.p, sd_idxs, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    DeviceZipIterator d_iter(thrust::make_tuple(thrust::device_pointer_cast(d_pos.p), thrust::device_pointer_cast(d_cp.p),
+                                                thrust::device_pointer_cast(d_si.p), thrust::device_pointer_cast(d_pi.p),
+                                                thrust::device_pointer_cast(d_index.p)));
+    int num_left = n, n_samples = 0, iteration = 0;
+    long long drawn = 0;
+    while (num_left > 0 && n_samples < max_samples) {
+        int blocks = (int)ceil((float)num_left / THREADS);
+        int n_batch = n_samples < 20000 ? 1000 : 100000;
+        n_samples += n_batch;
+        drawn += (long long)num_left * n_batch;
+        monte_carlo_sample_collision_dataset_uniform<<<blocks, THREADS>>>(d_robot.p, d_poses.p, d_sd.p, d_pi.p, d_si.p, d_pos.p, d_cp.p,
+                                                                          d_bins.p, d_acc.p, n_bins, d_done.p, iteration, n_samples,
+                                                                          n_batch, num_left, st.p);
+        int batch_done = thrust::count(thrust::device, thrust::device_pointer_cast(d_done.p), thrust::device_pointer_cast(d_done.p + num_left), 1);
+        if (batch_done > 0) {
+            thrust::sort_by_key(thrust::device_pointer_cast(d_done.p), thrust::device_pointer_cast(d_done.p + num_left), d_iter);
+            num_left -= batch_done;
+            write_collision_probability<<<(int)ceil((float)batch_done / THREADS), THREADS>>>(d_cp.p + num_left, batch_done, n_samples);
+            cudaMemcpy(pos.data() + num_left, d_pos.p + num_left, sizeof(Position) * batch_done, cudaMemcpyDeviceToHost);
+            cudaMemcpy(cp.data() + num_left, d_cp.p + num_left, sizeof(float) * batch_done, cudaMemcpyDeviceToHost);
+            cudaMemcpy(vi.data() + num_left, d_si.p + num_left, sizeof(float) * batch_done, cudaMemcpyDeviceToHost);
+            cudaMemcpy(pi.data() + num_left, d_pi.p + num_left, sizeof(float) * batch_done, cudaMemcpyDeviceToHost);
+            cudaMemcpy(index.data() + num_left, d_index.p + num_left, sizeof(int) * batch_done, cudaMemcpyDeviceToHost);
+        }
+        iteration++;
+    }
+    if (num_left > 0) {
+        write_collision_probability<<<(int)ceil((float)num_left / THREADS), THREADS>>>(d_cp.p, num_left, n_samples);
+        cudaMemcpy(cp.data(), d_cp.p, sizeof(float) * num_left, cudaMemcpyDeviceToHost);
+        cudaMemcpy(index.data(), d_index.p, sizeof(int) * num_left, cudaMemcpyDeviceToHost);
+    }
+    RG_CHECK(cudaDeviceSynchronize());
+    auto t1 = std::chrono::steady_clock::now();
+    RG_CHECK(cudaGetLastError());
+    for (int j = 0; j < n; j++) cp_out[index[j]] = cp[j];
+    *ms_out = std::chrono::duration<float, std::milli>(t1 - t0).count();
+    *samples_out = drawn;
     return 0;
 }
 

@@ -65,6 +65,27 @@ def test_adaptive_run_matches_stepwise_emulation(ctx, dev, oracle, workloads):
     assert len(set(want_ns.tolist())) > 3 and left.size > 0        # pairs really stop at different times, some never
 
 
+def test_adaptive_run_vs_reference_loop(ctx, dev, refgpu, workloads):
+    """The library's adaptive scheduler against the reference's own loop (its kernel + thrust::count +
+    thrust::sort_by_key, oracle/ref_gpu.cu::ref_adaptive_batch): independent RNGs, so statistical agreement:
+    |p1 - p2| <= 4.9 sqrt(2 p (1-p) / 1000) + 2e-3 (every pair used >= 1000 samples in both)."""
+    pairs = workloads.dataset_pairs(3000, seed=29)
+    rb, poses, sds, pi, si, pos = workloads.reference_tables(pairs)
+    bins = np.array([0, 0.01, 0.1, 1.0], np.float32); acc = np.array([1e-4, 1e-3, 1e-2], np.float32)
+    max_samples = 120_000
+    cp_ref, ms_ref, drawn_ref = refgpu.adaptive_batch(rb, poses, sds, pi, si, pos, bins, acc, max_samples, seed=4)
+    d = {k: dev.put(v) for k, v in dict(rb=rb, poses=poses.ravel(), sds=sds.ravel(), pi=pi, si=si, pos=pos.ravel(), bins=bins, acc=acc).items()}
+    d_cp = dev.zeros(pairs.size, np.float32)
+    iters, drawn = ctx.adaptive_run(d["rb"], d["poses"], pairs.size, d["sds"], pairs.size, d["pi"], d["si"], d["pos"], pairs.size,
+                                    d["bins"], d["acc"], 4, max_samples, 1000, 20000, 100000, 12345, d_cp)
+    ctx.synchronize()
+    cp = dev.get(d_cp)
+    p = (cp + cp_ref) / 2
+    assert np.all(np.abs(cp - cp_ref) <= 4.9 * np.sqrt(2 * p * (1 - p) / 1000) + 2e-3), np.abs(cp - cp_ref).max()
+    assert 0.5 < drawn / drawn_ref < 2.0                 # both schedules draw a similar number of samples
+    assert (cp_ref > 0).mean() > 0.02
+
+
 def test_sample_positions_ring_prior(ctx, dev, workloads):
     rng = np.random.default_rng(0)
     n_poses, n_std, n = 50, 40, 200_000
