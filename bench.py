@@ -37,9 +37,12 @@ PKG = "convex-2d-gpu-collision-detection_b200"
 
 METRIC = "SAT pair-tests/sec"
 UNIT = "tests/s"
-# FMA-pipe cost of one test in the fused 3-DoF loop, read off the SASS of k_count:
-# per 4-sample group 124 FP32 (FFMA/FMUL/FADD, 1 slot each) + 60 IMAD.WIDE (quarter rate on sm_100a: 4 slots)
-# = 364 FFMA-equivalent issue slots -> 91 per test.
+# Issue cost of one test in the fused 3-DoF loop, read off the SASS of k_count: per 4-sample
+# group 332 instructions, 60 of them IMAD.WIDE.  On sm_100a an IMAD.WIDE holds the warp scheduler's issue port for
+# ~4 cycles and does not overlap with FP32 issue (tools/ubench.cu: "IMAD.WIDE+LOP3+4 FFMA" = 9.4 clk, purely additive;
+# profiles/r1_ubench.log), so a group costs 272 + 60*4 = 512 issue slots = 128 lane-slots per test.
+ISSUE_SLOTS_PER_TEST = 128.0
+# FMA-pipe view of the same loop: 124 FP32 + 60 IMAD.WIDE x 4 = 364 FFMA-equivalent slots per group -> 91 per test
 FMA_SLOTS_PER_TEST = 91.0
 SURVEY_I_FMA_W8 = 247.0      # 8-axis kernel, 3-DoF
 SURVEY_I_FMA_W4 = 163.0      # 4-axis kernel (+ exact fallback), 3-DoF
@@ -306,15 +309,18 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
-                "bound": "fp32", "kernel": "satmc::k_count<DirectSrc,false> (fused, 3-DoF loop)",
-                "achieved": per_gpu * FMA_SLOTS_PER_TEST / 1e12, "peak": fma_peak / 1e12, "unit": "T FFMA-equivalent lane-slots/s",
-                "frac": per_gpu * FMA_SLOTS_PER_TEST / fma_peak, "traffic": 4.85e6,
-                "peak_source": f"148 SM x 128 lanes x sm_max_mhz {sm_mhz:.0f} from {src}",
-                "alg_units": "91 FMA-pipe issue slots per test (SASS: per 4-sample group 124 FP32 + 60 IMAD.WIDE x4)",
+                "bound": "fp32-issue", "kernel": "satmc::k_count<DirectSrc,false> (fused, 3-DoF loop)",
+                "achieved": per_gpu * ISSUE_SLOTS_PER_TEST / 1e12, "peak": fma_peak / 1e12, "unit": "T lane-issue-slots/s",
+                "frac": per_gpu * ISSUE_SLOTS_PER_TEST / fma_peak, "traffic": 4.86e6,
+                "peak_source": f"148 SM x 4 schedulers x 32 lanes x sm_max_mhz {sm_mhz:.0f} from {src} (= the FP32 lane peak)",
+                "alg_units": "128 issue slots per test: per 4-sample group 272 single-slot instructions + 60 IMAD.WIDE x 4 slots "
+                             "(IMAD.WIDE blocks issue ~4 clk on sm_100a, profiles/r1_ubench.log)",
+                "frac_fma_pipe": per_gpu * FMA_SLOTS_PER_TEST / fma_peak,
                 "frac_vs_survey_w8_model": per_gpu * SURVEY_I_FMA_W8 / fma_peak,
                 "frac_vs_survey_w4_model": per_gpu * SURVEY_I_FMA_W4 / fma_peak,
-                "note": "the fractions above 1 are against SURVEY.md section 8(d)'s instruction models (247 / 163 FMA-pipe "
-                        "instructions per test); this kernel needs ~46 (screening pass), so frac is quoted on its own SASS count",
+                "note": "frac = issue-slot utilisation on this kernel's own SASS count; frac_fma_pipe counts only FMA-pipe work "
+                        "(124 FP32 + 60 IMAD.WIDE x4 per group); the last two are against SURVEY.md 8(d)'s instruction models "
+                        "(247 / 163 FMA-pipe instructions per test) and exceed 1 because the screening pass needs ~46",
             },
             "hits_checksum": hits_total,
         }

@@ -35,6 +35,16 @@ __global__ void __launch_bounds__(1024, 1) k(uint32_t seed, uint32_t* sink, long
             if (OP == 13) { a[i] = __umulhi(a[i], 0xD2511F53u) + seed; }                                                    // IMAD.HI
             if (OP == 14) { uint64_t p = (uint64_t)a[i] * 0xD2511F53u + (uint64_t)a[(i + 1) % ILP]; a[i] = (uint32_t)(p >> 32); }  // IMAD.WIDE with add (chained on hi)
             if (OP == 15) { asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(f[i])); }                                     // MUFU.SQRT
+            if (OP == 17) { uint64_t p = (uint64_t)a[i] * 0xD2511F53u; a[i] = (uint32_t)p ^ (uint32_t)(p >> 32);            // 1 IMAD.WIDE + 1 LOP3 + 4 FFMA
+                            f[i] = fmaf(f[i], 1.0000001f, 1e-9f); f[i] = fmaf(f[i], 1.0000002f, 2e-9f);
+                            f[i] = fmaf(f[i], 1.0000003f, 3e-9f); f[i] = fmaf(f[i], 1.0000004f, 4e-9f); }
+            if (OP == 18) { uint64_t p = (uint64_t)a[i] * 0xD2511F53u; a[i] = (uint32_t)p ^ (uint32_t)(p >> 32);            // 1 IMAD.WIDE + 1 LOP3 + 8 FFMA
+                            f[i] = fmaf(f[i], 1.0000001f, 1e-9f); f[i] = fmaf(f[i], 1.0000002f, 2e-9f);
+                            f[i] = fmaf(f[i], 1.0000003f, 3e-9f); f[i] = fmaf(f[i], 1.0000004f, 4e-9f);
+                            f[i] = fmaf(f[i], 1.0000005f, 1e-9f); f[i] = fmaf(f[i], 1.0000006f, 2e-9f);
+                            f[i] = fmaf(f[i], 1.0000007f, 3e-9f); f[i] = fmaf(f[i], 1.0000008f, 4e-9f); }
+            if (OP == 19) { f[i] = fmaf(f[i], 1.0000001f, 1e-9f); f[i] = fmaf(f[i], 1.0000002f, 2e-9f);                      // 4 FFMA (baseline for 17)
+                            f[i] = fmaf(f[i], 1.0000003f, 3e-9f); f[i] = fmaf(f[i], 1.0000004f, 4e-9f); }
             if (OP == 16) { a[i] = __float_as_uint(f[i] = fmaf(f[i], 1.0000001f, 1e-9f)) >> 31; }                           // FFMA + SHF
         }
     }
@@ -66,6 +76,7 @@ int main()
 {
     run<3>("FFMA", 1); run<11>("FADD", 1); run<1>("IMAD", 1); run<0>("IMAD.WIDE+LOP3", 2); run<7>("IMAD.WIDE+IADD3", 2); run<2>("LOP3(x2)", 2);
     run<12>("I2F.U32+LOP3", 2); run<13>("IMAD.HI", 1); run<14>("IMAD.WIDE(+c)", 1); run<15>("MUFU.SQRT", 1);
+    run<19>("4 FFMA", 4); run<17>("IMAD.WIDE+LOP3+4 FFMA", 6); run<18>("IMAD.WIDE+LOP3+8 FFMA", 10);
     run<5>("PRMT", 1); run<6>("FMNMX+FMUL", 2); run<4>("MUFU.LG2", 1); run<8>("FMUL+MUFU.SIN", 2); run<9>("FFMA+IMAD", 2); run<10>("FFMA+LOP3x2", 3);
     return 0;
 }
