@@ -324,9 +324,9 @@ def main():
             },
             "hits_checksum": hits_total,
         }
-        if not args.no_extras and args.workload == "cfg3":
+        if world == 1 and not args.no_extras and args.workload == "cfg3":
             line["extras"] = extras(ctx, mod, wl, torch, hbm_peak, src)
-        if not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline:                # the CPU baseline is an N=1 measurement
             line["cpu_baseline"], _, _ = cpu_baseline(pairs, n_samples, seed)
         print(json.dumps(line), flush=True)
     lib = mod.load_library()
