@@ -851,12 +851,19 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
     const uint64_t resident_warps = (uint64_t)ctx->sm_count * bps * kWarps;
     const uint64_t target_items = resident_warps * 8;             // >= 8 items per resident warp when possible
     const uint64_t min_chunk = 2048;                              // 64 samples per lane: amortises the pair prologue
+    const uint64_t tiny_chunk = 256;                              // small problems: parallelism matters more than the prologue
     uint64_t n_chunks = 1;
     if (p.n_pairs < target_items) {
         n_chunks = (target_items + p.n_pairs - 1) / p.n_pairs;
         const uint64_t max_chunks = (p.n_samples + min_chunk - 1) / min_chunk;
         if (n_chunks > max_chunks) n_chunks = max_chunks;
         if (n_chunks < 1) n_chunks = 1;
+        if (p.n_pairs * n_chunks < resident_warps) {              // not even one item per resident warp: cut finer
+            uint64_t want = (resident_warps + p.n_pairs - 1) / p.n_pairs;
+            const uint64_t max_tiny = (p.n_samples + tiny_chunk - 1) / tiny_chunk;
+            if (want > max_tiny) want = max_tiny;
+            if (want > n_chunks) n_chunks = want;
+        }
     }
     if (n_chunks >= (uint64_t)kWarps) n_chunks = (n_chunks / kWarps) * kWarps;    // block-uniform pairs
     uint64_t chunk = (p.n_samples + n_chunks - 1) / n_chunks;
