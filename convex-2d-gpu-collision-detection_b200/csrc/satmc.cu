@@ -865,6 +865,8 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
             if (want > n_chunks) n_chunks = want;
         }
     }
+    const uint64_t max_chunk = 1ull << 36;                        // keeps the 32-bit per-lane counters exact (2^36 / 32 = 2^31)
+    if ((p.n_samples + n_chunks - 1) / n_chunks > max_chunk) n_chunks = (p.n_samples + max_chunk - 1) / max_chunk;
     if (n_chunks >= (uint64_t)kWarps) n_chunks = (n_chunks / kWarps) * kWarps;    // block-uniform pairs
     uint64_t chunk = (p.n_samples + n_chunks - 1) / n_chunks;
     chunk = ((chunk + 127) / 128) * 128;

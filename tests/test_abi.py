@@ -47,3 +47,20 @@ def test_product_does_not_reference_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "sat_oracle" not in text and "oracle/" not in text and "orc_" not in text, \
                     f"{f} references the oracle"
+
+
+def test_header_is_valid_c_and_links_from_c(satmc, tmp_path):
+    """include/satmc.h compiles as C99 and a plain C client links against libsatmc.so (no torch, no C++)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(satmc.LIB_PATH)
+    exe = str(tmp_path / "abi_example")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", satmc.INCLUDE_DIR,
+                           os.path.join(root, "tests", "c", "abi_example.c"), "-o", exe, "-L", libdir, "-lsatmc", "-lm",
+                           f"-Wl,-rpath,{libdir}"])
+    import torch
+    r = subprocess.run([exe], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 77, r.stdout + r.stderr       # fails loudly without a GPU

@@ -217,6 +217,27 @@ def test_adversarial_near_boundary(ctx, dev, oracle, satmc):
     assert np.any((want > 0) & (want < 4096))                     # and the cases really straddle the boundary
 
 
+def test_screening_equals_exact_on_4e10_samples(ctx, dev, workloads, satmc):
+    """Differential test of the screening pass at scale: four pair populations x 1e5 pairs x 1e5 fused samples,
+    counts with the screening pass == counts with every sample evaluated by the exact 8-axis arithmetic."""
+    rng = np.random.default_rng(123)
+    pops = []
+    pops.append(workloads.dataset_pairs(100_000, seed=201))                                  # the dataset prior
+    pops.append(workloads.dataset_pairs(100_000, seed=202, shape_variance=True))             # 5-DoF
+    p3 = workloads.dataset_pairs(100_000, seed=203)                                          # thin obstacles, tiny sigma, near contact
+    p3["ow"] = rng.uniform(0.01, 0.3, p3.size); p3["sd_x"] *= 0.05; p3["sd_y"] *= 0.05; p3["sd_theta"] *= 0.05
+    p3["rx"] *= 0.75; p3["ry"] *= 0.75
+    pops.append(p3)
+    p4 = workloads.dataset_pairs(100_000, seed=204, max_variance=4.0)                        # huge sigma (|dt| up to ~14 rad)
+    p4["rx"] = rng.uniform(-30, 30, p4.size); p4["ry"] = rng.uniform(-30, 30, p4.size)
+    pops.append(p4)
+    for k, pairs in enumerate(pops):
+        fast = fused(ctx, dev, pairs, 100_000, 900 + k)
+        exact = fused(ctx, dev, pairs, 100_000, 900 + k, flags=EXACT)
+        assert np.array_equal(fast, exact), (k, int((fast != exact).sum()))
+        assert fast.sum() > 0
+
+
 # ---- sampler ------------------------------------------------------------------------------------------
 def test_philox_kat_on_device(ctx, dev):
     from test_oracle import KAT

@@ -191,3 +191,15 @@ def test_program_errors(programs, tmp_path):
     assert r.returncode == 2 and "unrecognised option" in r.stderr
     r = subprocess.run([programs["generate_dataset"], "--help"], capture_output=True, text=True)
     assert r.returncode == 1 and "--num_batches" in r.stdout
+
+
+def test_plain_c_client(satmc, tmp_path):
+    """tests/c/abi_example.c (C99, no torch, no C++) runs the fused path through the C ABI on the GPU."""
+    libdir = os.path.dirname(satmc.LIB_PATH)
+    exe = str(tmp_path / "abi_example")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", satmc.INCLUDE_DIR,
+                           os.path.join(ROOT, "tests", "c", "abi_example.c"), "-o", exe, "-L", libdir, "-lsatmc", "-lm",
+                           f"-Wl,-rpath,{libdir}"])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "hits" in r.stdout
