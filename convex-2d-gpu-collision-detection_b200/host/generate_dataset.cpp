@@ -6,7 +6,9 @@
 // The Monte Carlo work goes through the satmc C ABI (no CUDA code here).  Differences from upstream, all
 // deliberate: the data directory is created before the first file is written (upstream writes
 // variances.npy first and fails if the directory is missing, :303 vs :343-345); --seed makes runs
-// reproducible (upstream seeds from time(0), :406); --device selects the GPU.
+// reproducible (upstream seeds from time(0), :406); --device selects the GPU; --gpus N spreads the batches
+// round-robin over N GPUs (one host thread and one satmc context per GPU; a batch's random streams depend
+// only on its number, so the files do not depend on N).
 #include <sys/stat.h>
 
 #include <algorithm>
@@ -15,8 +17,11 @@
 #include <cmath>
 #include <cstdio>
 #include <ctime>
+#include <atomic>
 #include <iostream>
+#include <mutex>
 #include <random>
+#include <thread>
 
 #include "cli.hpp"
 #include "npy.hpp"
@@ -34,7 +39,7 @@ struct Arguments {
     float robot_width = 4.07f, robot_height = 1.74f, spread = 4;
     bool shape_variance = false;
     long long seed = -1;
-    int device = 0;
+    int device = 0, gpus = 1;
 };
 
 static Arguments parse_args(int argc, char** argv) {
@@ -64,7 +69,8 @@ static Arguments parse_args(int argc, char** argv) {
      .add("pose_dir", Kind::String, "path of a poses .npy file to load instead of sampling")
      .add("variance_dir", Kind::String, "path of a variances .npy file to load instead of sampling")
      .add("seed", Kind::Int, "RNG seed (default: from the clock, as upstream)")
-     .add("device", Kind::Int, "CUDA device index");
+     .add("device", Kind::Int, "CUDA device index (first device when --gpus > 1)")
+     .add("gpus", Kind::Int, "number of GPUs to spread the batches over");
     p.parse(argc, argv);
     if (p.count("help")) { p.print_help(std::cout); std::cout << "\n"; exit(1); }
     if (p.count("data_dir")) a.data_dir = p.str("data_dir");
@@ -92,6 +98,8 @@ static Arguments parse_args(int argc, char** argv) {
     if (p.count("variance_dir")) a.variance_dir = p.str("variance_dir");
     if (p.count("seed")) a.seed = p.integer("seed");
     if (p.count("device")) a.device = p.integer("device");
+    if (p.count("gpus")) a.gpus = p.integer("gpus");
+    if (a.gpus < 1) throw std::runtime_error("--gpus must be >= 1");
     return a;
 }
 
@@ -153,34 +161,54 @@ int main(int argc, char* argv[]) try {
     npyio::save_f32(data_dir + "/meta/accuracy_bins.npy", {args.accuracy_bins.size()}, args.accuracy_bins);
     npyio::save_f32(data_dir + "/meta/bin_accuracy.npy", {args.bin_accuracy.size()}, args.bin_accuracy);
 
-    Context ctx(args.device);
-    MonteCarlo mc(ctx, args.robot_width, args.robot_height, poses, to_std_devs(variances), args.accuracy_bins, args.bin_accuracy);
+    const std::vector<StdDev> std_devs = to_std_devs(variances);
     const int B = args.batch_size;
-    DeviceArray<float> d_pos(ctx, 2 * (size_t)B), d_pose_idx(ctx, B), d_var_idx(ctx, B), d_cp(ctx, B);
     const float r_offset = (args.robot_width + args.robot_height) / 4;                    // :398
     const uint64_t seed = args.seed >= 0 ? (uint64_t)args.seed : (uint64_t)std::time(nullptr);
 
     auto begin = std::chrono::steady_clock::now();
     std::cout << "Total number of configurations: " << (long long)B * args.num_batches << std::endl;
     std::cout << "Begin computation..." << std::endl;
-    int counter = 0;
-    printf("batches generated: %i/%i", counter, args.num_batches);
-    std::vector<PoseCPVarAndPoseIdx> dataset(B);
-    for (int b = 0; b < args.num_batches; b++) {
-        const uint32_t stream = (uint32_t)(((uint64_t)(args.start_batch_count + b) * (uint64_t)B) & 0xffffffffu);
-        mc.sample_positions(B, r_offset, args.spread, seed, stream, d_pos, d_pose_idx, d_var_idx);
-        mc.run(d_pos, d_pose_idx, d_var_idx, B, Schedule::dataset(args.max_samples), seed, stream, d_cp);
-        std::vector<float> pos = d_pos.to_host(), pi = d_pose_idx.to_host(), vi = d_var_idx.to_host(), cp = d_cp.to_host();
-        for (int j = 0; j < B; j++) dataset[j] = {pos[2 * j], pos[2 * j + 1], cp[j], vi[j], pi[j]};   // :485-494
-        std::shuffle(dataset.begin(), dataset.end(), std::default_random_engine(0));                  // :496
-        npyio::save_f32(data_dir + "/" + std::to_string(args.start_batch_count + b) + ".npy", {(size_t)B, 5},
-                        reinterpret_cast<const float*>(dataset.data()));
-        auto end = std::chrono::steady_clock::now();
-        printf("\33[2K\r");
-        printf("batches generated: %i/%i, Time: %i [min]", ++counter, args.num_batches,
-               (int)std::chrono::duration_cast<std::chrono::minutes>(end - begin).count());
-        fflush(stdout);
-    }
+    std::atomic<int> counter{0};
+    std::mutex io;
+    std::string failure;
+    printf("batches generated: %i/%i", 0, args.num_batches);
+    fflush(stdout);
+
+    // one worker per GPU; worker w takes batches w, w + gpus, w + 2 gpus, ...
+    auto worker = [&](int w) {
+        try {
+            Context ctx(args.device + w);
+            MonteCarlo mc(ctx, args.robot_width, args.robot_height, poses, std_devs, args.accuracy_bins, args.bin_accuracy);
+            DeviceArray<float> d_pos(ctx, 2 * (size_t)B), d_pose_idx(ctx, B), d_var_idx(ctx, B), d_cp(ctx, B);
+            std::vector<PoseCPVarAndPoseIdx> dataset(B);
+            for (int b = w; b < args.num_batches; b += args.gpus) {
+                const uint32_t stream = (uint32_t)(((uint64_t)(args.start_batch_count + b) * (uint64_t)B) & 0xffffffffu);
+                mc.sample_positions(B, r_offset, args.spread, seed, stream, d_pos, d_pose_idx, d_var_idx);
+                mc.run(d_pos, d_pose_idx, d_var_idx, B, Schedule::dataset(args.max_samples), seed, stream, d_cp);
+                std::vector<float> pos = d_pos.to_host(), pi = d_pose_idx.to_host(), vi = d_var_idx.to_host(), cp = d_cp.to_host();
+                for (int j = 0; j < B; j++) dataset[j] = {pos[2 * j], pos[2 * j + 1], cp[j], vi[j], pi[j]};   // :485-494
+                std::shuffle(dataset.begin(), dataset.end(), std::default_random_engine(0));                  // :496
+                npyio::save_f32(data_dir + "/" + std::to_string(args.start_batch_count + b) + ".npy", {(size_t)B, 5},
+                                reinterpret_cast<const float*>(dataset.data()));
+                const int done = ++counter;
+                std::lock_guard<std::mutex> lock(io);
+                auto now = std::chrono::steady_clock::now();
+                printf("\33[2K\r");
+                printf("batches generated: %i/%i, Time: %i [min]", done, args.num_batches,
+                       (int)std::chrono::duration_cast<std::chrono::minutes>(now - begin).count());
+                fflush(stdout);
+            }
+        } catch (const std::exception& e) {
+            std::lock_guard<std::mutex> lock(io);
+            if (failure.empty()) failure = std::string("GPU ") + std::to_string(args.device + w) + ": " + e.what();
+        }
+    };
+    std::vector<std::thread> threads;
+    for (int w = 1; w < args.gpus; w++) threads.emplace_back(worker, w);
+    worker(0);
+    for (std::thread& t : threads) t.join();
+    if (!failure.empty()) throw std::runtime_error(failure);
     std::cout << std::endl;
     auto end = std::chrono::steady_clock::now();
     std::cout << "Finished computation" << std::endl;
