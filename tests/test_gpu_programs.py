@@ -184,6 +184,22 @@ def test_three_programs_end_to_end(programs, tmp_path, ctx, dev, workloads):
     assert np.all(np.abs(o1[:, 2] - b0[:1000, 2]) <= 4.9 * np.sqrt(2 * pp * (1 - pp) / 1000) + 2e-3)
 
 
+def test_generate_dataset_is_reproducible_and_gpu_count_invariant(programs, tmp_path, torch_cuda):
+    """Same --seed -> identical files; with >= 2 GPUs, --gpus 2 writes the same files as --gpus 1."""
+    common = ["-n", "3", "-b", "1500", "--num_poses", "200", "--num_variances", "200", "--max_samples", "30000", "--seed", "5"]
+    outs = []
+    runs = [["--gpus", "1"], ["--gpus", "1"]] + ([["--gpus", "2"]] if torch_cuda.cuda.device_count() >= 2 else [])
+    for k, extra in enumerate(runs):
+        d = tmp_path / f"run{k}"
+        r = subprocess.run([programs["generate_dataset"], "--data_dir", str(d)] + common + extra, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr + r.stdout
+        outs.append([np.load(d / f"{b}.npy") for b in range(3)])
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            np.testing.assert_array_equal(a, b)
+    assert not np.array_equal(outs[0][0], outs[0][1])              # different batches differ
+
+
 def test_program_errors(programs, tmp_path):
     r = subprocess.run([programs["ztest"], "--data_dir", str(tmp_path / "missing")], capture_output=True, text=True)
     assert r.returncode == 1 and "does not exist" in r.stdout
