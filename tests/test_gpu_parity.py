@@ -356,6 +356,36 @@ def test_fused_vs_reference_kernel_statistically(ctx, dev, refgpu, workloads):
     assert 0.02 < (cps > 0).mean()                                  # the workload has real hits
 
 
+# ---- BASELINE.json full sizes through size-independent properties ------------------------------------------
+def test_cfg4_full_size_sharding_property(ctx, dev, workloads):
+    """Single pair, N = 1e10: the count is the sum of the counts of 4 unequal sample ranges (what the NCCL all-reduce
+    adds up across ranks), and agrees with an independent 1e9-sample estimate within 4.9 sigma."""
+    pair = workloads.cfg2_pair()
+    n, seed = 10_000_000_000, 4
+    whole = int(fused(ctx, dev, pair, n, seed)[0])
+    cuts = [0, 1_234_567_891, 5_000_000_004, 5_000_000_005, n]
+    parts = sum(int(fused(ctx, dev, pair, b - a, seed, sample_offset=a)[0]) for a, b in zip(cuts[:-1], cuts[1:]))
+    assert parts == whole
+    k2 = int(fused(ctx, dev, pair, 1_000_000_000, seed + 1)[0])
+    p = whole / n
+    assert abs(k2 / 1e9 - p) < 4.9 * math.sqrt(p * (1 - p) * (1 / 1e9 + 1 / n))
+    assert 0.16 < p < 0.17
+
+
+def test_cfg5_full_size_streamed_vs_fused(ctx, dev, workloads):
+    """Variance sweep at full size (1e4 pairs x 64 covariances x 1e5 samples = 6.4e10 tests per path): the streamed path on a
+    shared bank of numpy normals and the fused path agree row by row within |k1 - k2| <= 4.9 sqrt(2 N p (1-p)) + 1."""
+    rows = workloads.variance_sweep_pairs(10_000, seed=5)
+    n = 100_000
+    z = workloads.normal_bank(n, 3, seed=55)
+    k_s = streamed(ctx, dev, rows, z).astype(np.float64)
+    k_f = fused(ctx, dev, rows, n, 2025).astype(np.float64)
+    p = (k_s + k_f) / (2 * n)
+    viol = np.abs(k_s - k_f) > 4.9 * np.sqrt(2 * n * p * (1 - p)) + 1
+    assert viol.sum() <= 2, int(viol.sum())                       # 6.4e5 rows at a 1e-6 two-sided level
+    assert rows.size == 640_000 and 0.02 < (k_f > 0).mean()
+
+
 # ---- reference-compatible step --------------------------------------------------------------------------
 def test_mc_step_matches_oracle_tail(ctx, dev, oracle, workloads):
     pairs = workloads.dataset_pairs(700, seed=15)
