@@ -38,7 +38,7 @@ ABI_SYMBOLS = (
     "satmc_create", "satmc_destroy", "satmc_synchronize", "satmc_last_error", "satmc_version",
     "satmc_launch_count", "satmc_set_profiling", "satmc_last_kernel_ms",
     "satmc_count_fused", "satmc_count_streamed", "satmc_decide_streamed", "satmc_fused_normals",
-    "satmc_philox_blocks", "satmc_sat_corners", "satmc_exact_evals",
+    "satmc_philox_blocks", "satmc_sat_corners", "satmc_exact_evals", "satmc_screen_debug",
     "satmc_mc_step", "satmc_write_collision_probability", "satmc_adaptive_run", "satmc_sample_positions",
     "satmc_device_alloc", "satmc_device_free", "satmc_upload", "satmc_download",
     "satmc_count_fused_host", "satmc_count_streamed_host", "satmc_collision_probability_host",
@@ -82,6 +82,7 @@ def load_library() -> ctypes.CDLL:
         "satmc_philox_blocks": (i32, [vp, vp, u64, u32, u32, vp]),
         "satmc_sat_corners": (i32, [vp, f32p, f32p, u64, vp]),
         "satmc_exact_evals": (i32, [vp, c.POINTER(u64), i32]),
+        "satmc_screen_debug": (i32, [vp, vp, f32p, u64, i32, u64, f32p, f32p]),
         "satmc_mc_step": (i32, [vp, f32p, f32p, u32, f32p, u32, f32p, f32p, f32p, f32p, f32p, f32p, i32, vp,
                                 i32, i32, i32, i32, u64, u32]),
         "satmc_write_collision_probability": (i32, [vp, f32p, i32, i32]),
@@ -197,6 +198,10 @@ class Context:
     def decide_streamed(self, d_pair, d_z, ldz, ndof, n_samples, d_out, flags=0):
         self._check(self._lib.satmc_decide_streamed(self._h, _ptr(d_pair), _ptr(d_z), ldz, ndof, n_samples,
                                                     _ptr(d_out), flags))
+
+    def screen_debug(self, d_pair, d_z, ldz, ndof, n_samples, d_m_out, d_eps_out):
+        self._check(self._lib.satmc_screen_debug(self._h, _ptr(d_pair), _ptr(d_z), ldz, ndof, n_samples, _ptr(d_m_out),
+                                                 _ptr(d_eps_out)))
 
     def fused_normals(self, seed, pair_id, sample_offset, n, ndof, d_z, ldz):
         self._check(self._lib.satmc_fused_normals(self._h, seed, pair_id, sample_offset, n, ndof, _ptr(d_z), ldz))

@@ -488,6 +488,27 @@ __global__ void k_decide(satmc_pair const* pair, const float* __restrict__ z, ui
 }
 
 // normals of samples [offset, offset+n) of stream pid, D planes (D = 3 or 5); one thread per group
+// diagnostics: the screening value m and the threshold it is compared with, per streamed sample of one pair
+__global__ void k_screen_debug(satmc_pair const* pair, const float* __restrict__ z, uint64_t ldz, int ndof, uint64_t n,
+                               float* m_out, float* eps_out)
+{
+    float v[12];
+    DirectSrc src{pair};
+    src.load(0, v);
+    PairConst P;
+    pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        float hmin;
+        if (ndof == 5) {
+            m_out[i] = screen_gap<5>(P, z[i], z[ldz + i], z[2 * ldz + i], z[3 * ldz + i], z[4 * ldz + i], hmin);
+            eps_out[i] = (hmin > 0.0f) ? P.eps_a + P.eps_b / hmin : CUDART_INF_F;
+        } else {
+            m_out[i] = screen_gap<3>(P, z[i], z[ldz + i], z[2 * ldz + i], 0.f, 0.f, hmin);
+            eps_out[i] = P.eps;
+        }
+    }
+}
+
 template <int D>
 __global__ void k_fused_normals(const __grid_constant__ PhiloxKeys K, uint32_t pid, uint64_t offset, uint64_t n, float* z, uint64_t ldz)
 {
@@ -953,6 +974,22 @@ int satmc_decide_streamed(satmc_ctx* ctx, const satmc_pair* d_pair, const float*
     uint64_t blocks = (n_samples + 255) / 256;
     if (blocks > (uint64_t)ctx->sm_count * 8) blocks = (uint64_t)ctx->sm_count * 8;
     k_decide<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_pair, d_z, ldz, ndof, n_samples, d_out, flags, ctx->d_exact_evals);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    return SATMC_OK;
+}
+
+int satmc_screen_debug(satmc_ctx* ctx, const satmc_pair* d_pair, const float* d_z, uint64_t ldz, int ndof, uint64_t n_samples,
+                       float* d_m_out, float* d_eps_out)
+{
+    int rc = check_streamed_args(ctx, d_pair, d_z, ldz, ndof, n_samples, 1, 0, d_m_out);
+    if (rc) return rc;
+    if (!d_eps_out) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
+    if (n_samples == 0) return SATMC_OK;
+    DeviceGuard g(ctx->device);
+    uint64_t blocks = (n_samples + 255) / 256;
+    if (blocks > (uint64_t)ctx->sm_count * 8) blocks = (uint64_t)ctx->sm_count * 8;
+    k_screen_debug<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_pair, d_z, ldz, ndof, n_samples, d_m_out, d_eps_out);
     CU(ctx, cudaGetLastError());
     ctx->launches++;
     return SATMC_OK;

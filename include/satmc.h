@@ -130,6 +130,12 @@ int satmc_philox_blocks(satmc_ctx* ctx, const uint32_t* d_ctr, uint64_t n, uint3
  *   replaces: convex_collide utils.cu:159-184 (BASELINE config 1 on the GPU) */
 int satmc_sat_corners(satmc_ctx* ctx, const float* d_r1, const float* d_r2, uint64_t n, uint8_t* d_out);
 
+/* Diagnostics: the screening value m (largest normalised signed gap) and the threshold it is
+ * compared with, for every supplied sample of ONE pair.  A sample is decided by the screening pass iff
+ * |m| > eps (and its normals are within the bound); tests use this to measure the safety margin of eps. */
+int satmc_screen_debug(satmc_ctx* ctx, const satmc_pair* d_pair, const float* d_z, uint64_t ldz, int ndof,
+                       uint64_t n_samples, float* d_m_out, float* d_eps_out);
+
 /* Diagnostics: number of samples that the screening pass could not decide and that were re-evaluated
  * with the exact arithmetic, accumulated over all counting calls since the last reset. */
 int satmc_exact_evals(satmc_ctx* ctx, uint64_t* out, int reset);

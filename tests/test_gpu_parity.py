@@ -217,6 +217,42 @@ def test_adversarial_near_boundary(ctx, dev, oracle, satmc):
     assert np.any((want > 0) & (want < 4096))                     # and the cases really straddle the boundary
 
 
+def test_screening_threshold_safety_margin(ctx, dev, oracle, satmc):
+    """Measures how far the screening value can be on the wrong side: over ~1.6e6 samples concentrated around first
+    contact (sigma comparable to eps), the largest |m| / eps among samples whose sign(m) disagrees with the exact
+    decision must stay well below 1 -- the threshold derived in DESIGN.md section 4 has a measured margin > 4x."""
+    rng = np.random.default_rng(77)
+    worst = 0.0; n_wrong = 0; n_band = 0
+    for trial in range(400):
+        five = trial % 2 == 1
+        ow, oh = rng.uniform(0.1, 5, 2); th = rng.uniform(0, 2 * np.pi); ang = rng.uniform(0, 2 * np.pi)
+        lo, hi = 0.0, 25.0
+        for _ in range(50):                                         # robot centre pushed to first contact along `ang`
+            mid = (lo + hi) / 2
+            p = satmc.pairs_from_columns(mid * math.cos(ang), mid * math.sin(ang), th, ow, oh, 0, 0, 0)
+            lo, hi = (mid, hi) if oracle.count_streamed(p, np.zeros((3, 1), np.float32)) else (lo, mid)
+        sig = 10.0 ** rng.uniform(-5.5, -3.5)
+        pair = satmc.pairs_from_columns(lo * math.cos(ang), lo * math.sin(ang), th, ow, oh, sig, sig, sig / 3,
+                                        sig if five else 0.0, sig if five else 0.0)
+        n, ndof = 4096, (5 if five else 3)
+        z = rng.standard_normal((ndof, n)).astype(np.float32)
+        d_pair, d_z = dev.put(pair), dev.put(z.ravel())
+        d_m, d_e = dev.zeros(n, np.float32), dev.zeros(n, np.float32)
+        d_dec = dev.zeros(n, np.uint8)
+        ctx.screen_debug(d_pair, d_z, n, ndof, n, d_m, d_e)
+        ctx.decide_streamed(d_pair, d_z, n, ndof, n, d_dec, flags=EXACT)
+        ctx.synchronize()
+        m, eps, exact = dev.get(d_m).astype(np.float64), dev.get(d_e).astype(np.float64), dev.get(d_dec).astype(bool)
+        wrong = (m < 0) != exact
+        n_wrong += int(wrong.sum()); n_band += int((np.abs(m) <= eps).sum())
+        if wrong.any():
+            worst = max(worst, float((np.abs(m[wrong]) / eps[wrong]).max()))
+    assert n_band > 100_000                                         # the samples really sit in the undecided band
+    assert n_wrong > 100                                            # and the screening sign really is unreliable there
+    print(f"screening margin: worst |m|/eps among {n_wrong} wrong-sign samples = {worst:.4f}; {n_band} samples in the undecided band")
+    assert worst < 0.25, worst
+
+
 def test_screening_equals_exact_on_4e10_samples(ctx, dev, workloads, satmc):
     """Differential test of the screening pass at scale: four pair populations x 1e5 pairs x 1e5 fused samples,
     counts with the screening pass == counts with every sample evaluated by the exact 8-axis arithmetic."""
