@@ -33,12 +33,19 @@ PAIR_DTYPE = np.dtype([(n, "<f4") for n in
                        ("rx", "ry", "rtheta", "rw", "rh", "ow", "oh", "sd_x", "sd_y", "sd_theta", "sd_w", "sd_h")])
 PAIR_FIELDS = PAIR_DTYPE.names
 
+#: numpy dtype of ``satmc_poly_pair`` -- 160 bytes
+POLY_MAX = 8
+POLY_PAIR_DTYPE = np.dtype([("rx", "<f4"), ("ry", "<f4"), ("rtheta", "<f4"), ("sd_x", "<f4"), ("sd_y", "<f4"), ("sd_theta", "<f4"),
+                            ("n_robot", "<u4"), ("n_obstacle", "<u4"), ("robot", "<f4", (2 * POLY_MAX,)),
+                            ("obstacle", "<f4", (2 * POLY_MAX,))])
+
 #: every symbol include/satmc.h declares (checked against the built library by tests/test_abi.py)
 ABI_SYMBOLS = (
     "satmc_create", "satmc_destroy", "satmc_synchronize", "satmc_last_error", "satmc_version",
     "satmc_launch_count", "satmc_set_profiling", "satmc_last_kernel_ms",
     "satmc_count_fused", "satmc_count_streamed", "satmc_decide_streamed", "satmc_fused_normals",
     "satmc_philox_blocks", "satmc_sat_corners", "satmc_exact_evals", "satmc_screen_debug",
+    "satmc_count_fused_polygons", "satmc_count_streamed_polygons",
     "satmc_mc_step", "satmc_write_collision_probability", "satmc_adaptive_run", "satmc_sample_positions",
     "satmc_device_alloc", "satmc_device_free", "satmc_upload", "satmc_download",
     "satmc_count_fused_host", "satmc_count_streamed_host", "satmc_collision_probability_host",
@@ -83,6 +90,8 @@ def load_library() -> ctypes.CDLL:
         "satmc_sat_corners": (i32, [vp, f32p, f32p, u64, vp]),
         "satmc_exact_evals": (i32, [vp, c.POINTER(u64), i32]),
         "satmc_screen_debug": (i32, [vp, vp, f32p, u64, i32, u64, f32p, f32p]),
+        "satmc_count_fused_polygons": (i32, [vp, vp, u64, u64, u64, u64, u32, vp, u32]),
+        "satmc_count_streamed_polygons": (i32, [vp, vp, u64, f32p, u64, u64, u64, vp, u32]),
         "satmc_mc_step": (i32, [vp, f32p, f32p, u32, f32p, u32, f32p, f32p, f32p, f32p, f32p, f32p, i32, vp,
                                 i32, i32, i32, i32, u64, u32]),
         "satmc_write_collision_probability": (i32, [vp, f32p, i32, i32]),
@@ -120,6 +129,22 @@ def pairs_from_columns(rx, ry, rtheta, ow, oh, sd_x, sd_y, sd_theta, sd_w=0.0, s
     out = make_pairs(cols[0].size)
     for name, col in zip(PAIR_FIELDS, cols):
         out[name] = col.ravel()
+    return out
+
+
+def make_poly_pairs(robots, obstacles, rx, ry, rtheta, sd_x, sd_y, sd_theta) -> np.ndarray:
+    """Polygon pair array: `robots` / `obstacles` are sequences of [k,2] CCW vertex arrays (k <= 8), the rest broadcast."""
+    n = len(robots)
+    out = np.zeros(n, dtype=POLY_PAIR_DTYPE)
+    cols = np.broadcast_arrays(*[np.asarray(a, dtype=np.float32) for a in (rx, ry, rtheta, sd_x, sd_y, sd_theta)], np.zeros(n, np.float32))
+    for name, col in zip(("rx", "ry", "rtheta", "sd_x", "sd_y", "sd_theta"), cols):
+        out[name] = col
+    for i, (r, o) in enumerate(zip(robots, obstacles)):
+        r = np.asarray(r, np.float32).reshape(-1, 2); o = np.asarray(o, np.float32).reshape(-1, 2)
+        if not (1 <= len(r) <= POLY_MAX and 1 <= len(o) <= POLY_MAX):
+            raise ValueError("polygons need 1..8 vertices")
+        out["n_robot"][i] = len(r); out["n_obstacle"][i] = len(o)
+        out["robot"][i, :2 * len(r)] = r.ravel(); out["obstacle"][i, :2 * len(o)] = o.ravel()
     return out
 
 
@@ -194,6 +219,14 @@ class Context:
     def count_streamed(self, d_pairs, n_pairs, d_z, ldz, ndof, n_samples, d_hits, z_pair_stride=0, flags=0):
         self._check(self._lib.satmc_count_streamed(self._h, _ptr(d_pairs), n_pairs, _ptr(d_z), ldz, z_pair_stride,
                                                    ndof, n_samples, _ptr(d_hits), flags))
+
+    def count_fused_polygons(self, d_pairs, n_pairs, n_samples, seed, d_hits, sample_offset=0, pair_id_offset=0, flags=0):
+        self._check(self._lib.satmc_count_fused_polygons(self._h, _ptr(d_pairs), n_pairs, n_samples, seed, sample_offset,
+                                                         pair_id_offset, _ptr(d_hits), flags))
+
+    def count_streamed_polygons(self, d_pairs, n_pairs, d_z, ldz, n_samples, d_hits, z_pair_stride=0, flags=0):
+        self._check(self._lib.satmc_count_streamed_polygons(self._h, _ptr(d_pairs), n_pairs, _ptr(d_z), ldz, z_pair_stride,
+                                                            n_samples, _ptr(d_hits), flags))
 
     def decide_streamed(self, d_pair, d_z, ldz, ndof, n_samples, d_out, flags=0):
         self._check(self._lib.satmc_decide_streamed(self._h, _ptr(d_pair), _ptr(d_z), ldz, ndof, n_samples,

@@ -19,6 +19,7 @@
 #include <new>
 
 #include "satmc_geom.cuh"
+#include "satmc_poly.cuh"
 #include "satmc_sampler.cuh"
 
 namespace satmc {
@@ -463,6 +464,65 @@ k_count_streamed_tma(const __grid_constant__ DirectSrc src, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
+// general convex polygons: same work decomposition, sampler and counting as k_count;
+// every sample is evaluated with the exact polygon SAT of satmc_poly.cuh (no screening pass yet)
+// ---------------------------------------------------------------------------------------------
+template <bool STREAMED>
+__global__ void __launch_bounds__(kThreads, 2) k_count_poly(const float* __restrict__ pairs, const __grid_constant__ CountParams p)
+{
+    __shared__ PolyPairShared s_poly[kWarps];
+    __shared__ unsigned s_part[kWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t)gridDim.x * kWarps;
+    for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < p.n_items; item += stride) {
+        const uint64_t pair = item / p.n_chunks;
+        const uint32_t chunk_id = (uint32_t)(item - pair * p.n_chunks);
+        __syncwarp();
+        if (lane == 0) poly_prologue(s_poly[warp], pairs + pair * 40);          // 160-byte descriptors
+        __syncwarp();
+        const PolyPairShared& S = s_poly[warp];
+        const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
+        const uint64_t c_len = (c_begin + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - c_begin);
+        unsigned cnt = 0;
+        if (STREAMED) {
+            const float* z = p.z + pair * p.z_pair_stride + c_begin;
+            for (uint64_t i = (uint64_t)lane; i < c_len; i += 32)
+                cnt += poly_collide(S, __ldg(z + i), __ldg(z + p.ldz + i), __ldg(z + 2 * p.ldz + i));
+        } else {
+            const uint32_t pid = p.pair_id_offset + (uint32_t)pair;
+            const uint64_t b = p.sample_offset + c_begin, e = b + c_len;
+            for (uint64_t g = (b >> 2) + (uint64_t)lane; 4 * g < e; g += 32) {    // 4-sample groups, ragged ends masked
+                float n[12];
+                group_normals<3>((uint32_t)g, (uint32_t)(g >> 32), pid, p.keys, n);
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const uint64_t sidx = 4 * g + t;
+                    if (sidx >= b && sidx < e) cnt += poly_collide(S, n[3 * t], n[3 * t + 1], n[3 * t + 2]);
+                }
+            }
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (p.block_uniform) {
+            if (lane == 0) s_part[warp] = cnt;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long t = 0;
+#pragma unroll
+                for (int w = 0; w < kWarps; w++) t += s_part[w];
+                atomicAdd(p.hits + pair, t);
+            }
+            __syncthreads();
+        } else if (lane == 0) {
+            if (p.n_chunks == 1) {
+                if (p.flags & SATMC_ACCUMULATE) p.hits[pair] += cnt; else p.hits[pair] = cnt;
+            } else {
+                atomicAdd(p.hits + pair, (unsigned long long)cnt);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // small kernels
 // ---------------------------------------------------------------------------------------------
 __global__ void k_decide(satmc_pair const* pair, const float* __restrict__ z, uint64_t ldz, int ndof, uint64_t n,
@@ -855,20 +915,9 @@ int satmc_exact_evals(satmc_ctx* ctx, uint64_t* out, int reset)
 
 }  // extern "C"
 
-// Chooses chunking and launches the counting kernel.
-template <class Src, bool STREAMED>
-static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time_it)
+// Chooses the chunking of the sample range (work item = (pair, chunk), one warp per item) and the grid size.
+static int plan_items(satmc_ctx* ctx, CountParams& p, int bps, uint64_t& blocks)
 {
-    if (p.n_pairs == 0 || p.n_samples == 0) {
-        if (p.n_pairs && !(p.flags & SATMC_ACCUMULATE))
-            CU(ctx, cudaMemsetAsync(p.hits, 0, p.n_pairs * sizeof(unsigned long long), ctx->stream));
-        return SATMC_OK;
-    }
-    // bulk-tensor path: aligned bank, coordinates that fit the TMA's 32-bit signed indices, a driver that encodes the map
-    CUtensorMap zmap;
-    bool tma = STREAMED && p.vec_ok && p.ldz < (1ull << 31) && p.ldz >= (uint64_t)kTile;
-    if (tma) tma = make_z_tensor_map(&zmap, p.z, p.ldz, p.ndof);
-    const int bps = tma ? ctx->blocks_per_sm_tma[p.ndof == 5] : (STREAMED ? ctx->blocks_per_sm_streamed : ctx->blocks_per_sm);
     const uint64_t resident_warps = (uint64_t)ctx->sm_count * bps * kWarps;
     const uint64_t target_items = resident_warps * 8;             // >= 8 items per resident warp when possible
     const uint64_t min_chunk = 2048;                              // 64 samples per lane: amortises the pair prologue
@@ -899,9 +948,29 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
     p.block_uniform = (n_chunks % kWarps == 0) ? 1u : 0u;
     if (n_chunks > 1 && !(p.flags & SATMC_ACCUMULATE))
         CU(ctx, cudaMemsetAsync(p.hits, 0, p.n_pairs * sizeof(unsigned long long), ctx->stream));
-    uint64_t blocks = (p.n_items + kWarps - 1) / kWarps;
+    blocks = (p.n_items + kWarps - 1) / kWarps;
     const uint64_t max_blocks = (uint64_t)ctx->sm_count * bps;
     if (blocks > max_blocks) blocks = max_blocks;
+    return SATMC_OK;
+}
+
+// Launches the rectangle counting kernel.
+template <class Src, bool STREAMED>
+static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time_it)
+{
+    if (p.n_pairs == 0 || p.n_samples == 0) {
+        if (p.n_pairs && !(p.flags & SATMC_ACCUMULATE))
+            CU(ctx, cudaMemsetAsync(p.hits, 0, p.n_pairs * sizeof(unsigned long long), ctx->stream));
+        return SATMC_OK;
+    }
+    // bulk-tensor path: aligned bank, coordinates that fit the TMA's 32-bit signed indices, a driver that encodes the map
+    CUtensorMap zmap;
+    bool tma = STREAMED && p.vec_ok && p.ldz < (1ull << 31) && p.ldz >= (uint64_t)kTile;
+    if (tma) tma = make_z_tensor_map(&zmap, p.z, p.ldz, p.ndof);
+    const int bps = tma ? ctx->blocks_per_sm_tma[p.ndof == 5] : (STREAMED ? ctx->blocks_per_sm_streamed : ctx->blocks_per_sm);
+    uint64_t blocks = 0;
+    int rc = plan_items(ctx, p, bps, blocks);
+    if (rc) return rc;
     if (time_it) CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if constexpr (STREAMED) {
         if (tma && p.ndof == 5)
@@ -1034,6 +1103,53 @@ int satmc_sat_corners(satmc_ctx* ctx, const float* d_r1, const float* d_r2, uint
     if (n == 0) return SATMC_OK;
     DeviceGuard g(ctx->device);
     k_sat_corners<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_r1, d_r2, n, d_out);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    return SATMC_OK;
+}
+
+int satmc_count_fused_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs, uint64_t n_pairs, uint64_t n_samples, uint64_t seed,
+                               uint64_t sample_offset, uint32_t pair_id_offset, uint64_t* d_hits, uint32_t flags)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    if ((!d_pairs || !d_hits) && n_pairs) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
+    if (n_pairs > 0xffffffffull - pair_id_offset) return fail(ctx, SATMC_ERR_INVALID, "pair ids exceed 32 bits");
+    DeviceGuard g(ctx->device);
+    CountParams p{};
+    p.n_pairs = n_pairs; p.n_samples = n_samples; p.sample_offset = sample_offset; p.pair_id_offset = pair_id_offset;
+    philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), p.keys); p.flags = flags & SATMC_ACCUMULATE;
+    p.hits = reinterpret_cast<unsigned long long*>(d_hits);
+    if (n_pairs == 0 || n_samples == 0) {
+        if (n_pairs && !(flags & SATMC_ACCUMULATE)) CU(ctx, cudaMemsetAsync(d_hits, 0, n_pairs * sizeof(uint64_t), ctx->stream));
+        return SATMC_OK;
+    }
+    uint64_t blocks = 0;
+    int rc = plan_items(ctx, p, 2, blocks);
+    if (rc) return rc;
+    k_count_poly<false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(reinterpret_cast<const float*>(d_pairs), p);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    return SATMC_OK;
+}
+
+int satmc_count_streamed_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs, uint64_t n_pairs, const float* d_z, uint64_t ldz,
+                                  uint64_t z_pair_stride, uint64_t n_samples, uint64_t* d_hits, uint32_t flags)
+{
+    int rc = check_streamed_args(ctx, d_pairs, d_z, ldz, 3, n_samples, n_pairs, z_pair_stride, d_hits);
+    if (rc) return rc;
+    DeviceGuard g(ctx->device);
+    CountParams p{};
+    p.n_pairs = n_pairs; p.n_samples = n_samples; p.flags = flags & SATMC_ACCUMULATE;
+    p.hits = reinterpret_cast<unsigned long long*>(d_hits);
+    p.z = d_z; p.ldz = ldz; p.z_pair_stride = z_pair_stride; p.ndof = 3;
+    if (n_pairs == 0 || n_samples == 0) {
+        if (n_pairs && !(flags & SATMC_ACCUMULATE)) CU(ctx, cudaMemsetAsync(d_hits, 0, n_pairs * sizeof(uint64_t), ctx->stream));
+        return SATMC_OK;
+    }
+    uint64_t blocks = 0;
+    rc = plan_items(ctx, p, 2, blocks);
+    if (rc) return rc;
+    k_count_poly<true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(reinterpret_cast<const float*>(d_pairs), p);
     CU(ctx, cudaGetLastError());
     ctx->launches++;
     return SATMC_OK;

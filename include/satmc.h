@@ -140,6 +140,31 @@ int satmc_screen_debug(satmc_ctx* ctx, const satmc_pair* d_pair, const float* d_
  * with the exact arithmetic, accumulated over all counting calls since the last reset. */
 int satmc_exact_evals(satmc_ctx* ctx, uint64_t* out, int reset);
 
+/* ---- general convex polygons ---------------------------------------------------------------- */
+
+/* The reference handles rectangles only and notes that SAT "can easily be extended" to other convex shapes
+ * (README.md:3).  These entry points are that extension: robot and obstacle are convex polygons with 1..8
+ * counter-clockwise vertices; the obstacle's pose is perturbed by z0*sd_x, z1*sd_y, z2*sd_theta exactly as
+ * sample_rectangle does (utils.cu:144-157, no shape perturbation); the separating axes are the true edge normals
+ * of both polygons (convex_collide's edge directions, utils.cu:170-171, are valid axes only for rectangles);
+ * projections, strict-< separation and tie/NaN behaviour follow utils.cu:172-181.  160 bytes, 16-byte aligned. */
+#define SATMC_POLY_MAX 8
+typedef struct satmc_poly_pair {
+    float rx, ry, rtheta;              /* robot pose in the obstacle's nominal frame                      */
+    float sd_x, sd_y, sd_theta;        /* standard deviations of the obstacle pose perturbation            */
+    uint32_t n_robot, n_obstacle;      /* vertex counts, 1..SATMC_POLY_MAX                                 */
+    float robot[2 * SATMC_POLY_MAX];   /* robot vertices x0,y0,.. in the robot's own frame                 */
+    float obstacle[2 * SATMC_POLY_MAX];/* obstacle vertices in its nominal frame                           */
+} satmc_poly_pair;
+
+/* Same semantics as satmc_count_fused / satmc_count_streamed (3 normals per sample: x, y, theta). */
+int satmc_count_fused_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs, uint64_t n_pairs,
+                               uint64_t n_samples, uint64_t seed, uint64_t sample_offset,
+                               uint32_t pair_id_offset, uint64_t* d_hits, uint32_t flags);
+int satmc_count_streamed_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs, uint64_t n_pairs,
+                                  const float* d_z, uint64_t ldz, uint64_t z_pair_stride,
+                                  uint64_t n_samples, uint64_t* d_hits, uint32_t flags);
+
 /* ---- reference-compatible Monte Carlo step ------------------------------------------------- */
 
 /* One launch of the reference kernel, same argument meaning as

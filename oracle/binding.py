@@ -52,6 +52,8 @@ class Oracle:
         L.orc_count_streamed.restype = C.c_uint64
         L.orc_count_streamed.argtypes = [fp, fp, C.c_size_t, C.c_int, C.c_size_t, u8p]
         L.orc_count_streamed_batch.argtypes = [fp, C.c_size_t, fp, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, u64p, C.c_int]
+        L.orc_poly_count_streamed.restype = C.c_uint64
+        L.orc_poly_count_streamed.argtypes = [fp, fp, C.c_size_t, C.c_size_t, u8p]
         L.orc_philox4x32_10.argtypes = [fp, fp, fp]
         L.orc_fused_normals.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, fp]
         L.orc_count_fused_batch.argtypes = [fp, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, u64p, C.c_int]
@@ -129,6 +131,16 @@ class Oracle:
                                    z.shape[1], int(n_batch), int(n_samples_total), b.ctypes.data, a.ctypes.data,
                                    len(bins), C.byref(done))
         return int(k), int(done.value)
+
+    def poly_count_streamed(self, poly_pair, z, want_decisions=False):
+        """poly_pair: one element of the 160-byte polygon pair dtype; z: [3, n] float32."""
+        p = np.ascontiguousarray(poly_pair).reshape(1)
+        assert p.dtype.itemsize == 160
+        z = _f32(z)
+        n = z.shape[1]
+        dec = np.zeros(n, np.uint8) if want_decisions else None
+        h = self.lib.orc_poly_count_streamed(p.ctypes.data, z.ctypes.data, n, n, dec.ctypes.data if want_decisions else None)
+        return (int(h), dec) if want_decisions else int(h)
 
     def philox(self, ctr, key):
         ctr = np.ascontiguousarray(ctr, np.uint32); key = np.ascontiguousarray(key, np.uint32)

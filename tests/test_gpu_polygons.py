@@ -1,0 +1,118 @@
+"""GPU box: general convex polygons against the oracle's restatement, the rectangle path and an
+independent float64 check."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def regular(k, r, phase=0.0):
+    a = phase + 2 * np.pi * np.arange(k) / k
+    return np.stack([r * np.cos(a), r * np.sin(a)], 1).astype(np.float32)
+
+
+def rect_poly(w, h):
+    return np.array([[-w / 2, -h / 2], [w / 2, -h / 2], [w / 2, h / 2], [-w / 2, h / 2]], np.float32)
+
+
+def random_convex(rng, k, r):
+    a = np.sort(rng.uniform(0, 2 * np.pi, k))
+    rad = r * rng.uniform(0.6, 1.0, k)
+    pts = np.stack([rad * np.cos(a), rad * np.sin(a)], 1)
+    # convex hull of points on a star-shaped ring is not guaranteed convex: project on the circle to keep convexity
+    return np.stack([r * np.cos(a), r * np.sin(a)], 1).astype(np.float32) if k > 3 else pts.astype(np.float32)
+
+
+def poly_count(ctx, dev, pp, z=None, n=None, seed=None, **kw):
+    d_pairs = dev.put(pp.view(np.uint8).view(np.float32))
+    d_hits = dev.zeros(pp.size, np.uint64)
+    if z is not None:
+        ctx.count_streamed_polygons(d_pairs, pp.size, dev.put(z.ravel()), z.shape[1], z.shape[1], d_hits, **kw)
+    else:
+        ctx.count_fused_polygons(d_pairs, pp.size, n, seed, d_hits, **kw)
+    ctx.synchronize()
+    return dev.get(d_hits, np.uint64)
+
+
+def test_polygon_decisions_match_oracle_bit_for_bit(ctx, dev, oracle, satmc):
+    rng = np.random.default_rng(5)
+    robots, obstacles = [], []
+    for i in range(60):
+        kr, ko = rng.integers(3, 9), rng.integers(3, 9)
+        robots.append(random_convex(rng, kr, rng.uniform(0.5, 2.5)))
+        obstacles.append(random_convex(rng, ko, rng.uniform(0.3, 2.5)))
+    robots += [regular(1, 0.0), regular(2, 1.0), rect_poly(4.07, 1.74)]          # point, segment, the reference robot
+    obstacles += [regular(5, 1.0), regular(8, 1.5), regular(1, 0.0)]
+    n = len(robots)
+    d = rng.uniform(0.5, 5.0, n); ang = rng.uniform(0, 2 * np.pi, n)
+    pp = satmc.make_poly_pairs(robots, obstacles, d * np.cos(ang), d * np.sin(ang), rng.uniform(0, 6.28, n),
+                               rng.uniform(0.05, 0.6, n), rng.uniform(0.05, 0.6, n), rng.uniform(0.0, 0.6, n))
+    for ns in (1, 33, 1000, 2051):
+        z = rng.standard_normal((3, ns)).astype(np.float32)
+        want = np.array([oracle.poly_count_streamed(pp[i], z) for i in range(n)], np.uint64)
+        np.testing.assert_array_equal(poly_count(ctx, dev, pp, z=z), want)
+    assert 0 < want.sum() < n * 2051
+
+
+def test_polygon_path_agrees_with_rectangle_path_on_rectangles(ctx, dev, workloads, satmc):
+    """4-vertex polygons built from the rectangle workload: true edge normals vs the reference's edge directions are the
+    same axis set for rectangles, so counts agree except for samples within rounding of a tie."""
+    pairs = workloads.dataset_pairs(400, seed=61)
+    robots = [rect_poly(p["rw"], p["rh"]) for p in pairs]
+    obstacles = [rect_poly(p["ow"], p["oh"]) for p in pairs]
+    pp = satmc.make_poly_pairs(robots, obstacles, pairs["rx"], pairs["ry"], pairs["rtheta"], pairs["sd_x"], pairs["sd_y"], pairs["sd_theta"])
+    n = 20_000
+    z = workloads.normal_bank(n, 3, seed=62)
+    k_poly = poly_count(ctx, dev, pp, z=z).astype(np.int64)
+    d_hits = dev.zeros(pairs.size, np.uint64)
+    ctx.count_streamed(dev.put(pairs), pairs.size, dev.put(z.ravel()), n, 3, n, d_hits)
+    ctx.synchronize()
+    k_rect = dev.get(d_hits, np.uint64).astype(np.int64)
+    assert np.abs(k_poly - k_rect).max() <= 1 and (k_poly != k_rect).sum() <= 3
+    # the fused polygon path consumes the same Philox stream as the fused rectangle path (3 normals per sample)
+    kf_poly = poly_count(ctx, dev, pp, n=n, seed=9, sample_offset=5, pair_id_offset=3).astype(np.int64)
+    ctx.count_fused(dev.put(pairs), pairs.size, n, 9, d_hits, sample_offset=5, pair_id_offset=3)
+    ctx.synchronize()
+    kf_rect = dev.get(d_hits, np.uint64).astype(np.int64)
+    assert np.abs(kf_poly - kf_rect).max() <= 1 and (kf_poly != kf_rect).sum() <= 3
+
+
+def test_polygon_fused_sharding_and_float64_probability(ctx, dev, satmc):
+    rng = np.random.default_rng(8)
+    robots = [regular(6, 1.5, 0.3)] * 4
+    obstacles = [regular(5, 1.2, 0.1), regular(3, 1.0), regular(8, 0.8), rect_poly(2.0, 0.7)]
+    pp = satmc.make_poly_pairs(robots, obstacles, [2.4, 2.0, 2.1, 2.3], [0.3, -0.5, 0.2, 0.0], [0.2, 1.0, 2.0, 0.5], 0.4, 0.3, 0.5)
+    n, seed = 400_000, 17
+    whole = poly_count(ctx, dev, pp, n=n, seed=seed)
+    parts = poly_count(ctx, dev, pp, n=123_457, seed=seed) + poly_count(ctx, dev, pp, n=n - 123_457, seed=seed, sample_offset=123_457)
+    np.testing.assert_array_equal(whole, parts)
+    # independent float64 Monte Carlo with numpy (true normals, separating axis)
+    def sat64(A, B):
+        for P, Q in ((A, B), (B, A)):
+            e = np.roll(P, -1, axis=1) - P
+            nrm = np.stack([e[..., 1], -e[..., 0]], -1)
+            pa = np.einsum("nik,njk->nij", nrm, A); pb = np.einsum("nik,njk->nij", nrm, B)
+            if P is A:
+                sep = (pa.max(2) < pb.min(2)) | (pb.max(2) < pa.min(2))
+            else:
+                sep = sep | ((pa.max(2) < pb.min(2)) | (pb.max(2) < pa.min(2))).any(1, keepdims=True) if False else sep
+            yield (pa.max(2) < pb.min(2)) | (pb.max(2) < pa.min(2))
+    m = 200_000
+    for i in range(pp.size):
+        zz = rng.standard_normal((3, m))
+        R = pp["robot"][i][:2 * pp["n_robot"][i]].reshape(-1, 2).astype(np.float64)
+        O = pp["obstacle"][i][:2 * pp["n_obstacle"][i]].reshape(-1, 2).astype(np.float64)
+        th = float(pp["rtheta"][i]); c0, s0 = math.cos(th), math.sin(th)
+        Rw = np.stack([c0 * R[:, 0] - s0 * R[:, 1] + pp["rx"][i], s0 * R[:, 0] + c0 * R[:, 1] + pp["ry"][i]], 1)
+        dt = zz[2] * pp["sd_theta"][i]; c, s = np.cos(dt)[:, None], np.sin(dt)[:, None]
+        Ow = np.stack([c * O[None, :, 0] - s * O[None, :, 1] + (zz[0] * pp["sd_x"][i])[:, None],
+                       s * O[None, :, 0] + c * O[None, :, 1] + (zz[1] * pp["sd_y"][i])[:, None]], 2)
+        A = np.broadcast_to(Rw, (m,) + Rw.shape)
+        seps = list(sat64(A, Ow))
+        hit = ~(seps[0].any(1) | seps[1].any(1))
+        p_ref = hit.mean(); p = whole[i] / n
+        pm = (p + p_ref) / 2
+        assert abs(p - p_ref) < 4.9 * math.sqrt(pm * (1 - pm) * (1 / n + 1 / m)) + 1e-9, (i, p, p_ref)
+    assert 0.01 < (whole / n).min() and (whole / n).max() < 0.99
