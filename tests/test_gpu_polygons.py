@@ -89,16 +89,12 @@ def test_polygon_fused_sharding_and_float64_probability(ctx, dev, satmc):
     parts = poly_count(ctx, dev, pp, n=123_457, seed=seed) + poly_count(ctx, dev, pp, n=n - 123_457, seed=seed, sample_offset=123_457)
     np.testing.assert_array_equal(whole, parts)
     # independent float64 Monte Carlo with numpy (true normals, separating axis)
-    def sat64(A, B):
-        for P, Q in ((A, B), (B, A)):
-            e = np.roll(P, -1, axis=1) - P
-            nrm = np.stack([e[..., 1], -e[..., 0]], -1)
-            pa = np.einsum("nik,njk->nij", nrm, A); pb = np.einsum("nik,njk->nij", nrm, B)
-            if P is A:
-                sep = (pa.max(2) < pb.min(2)) | (pb.max(2) < pa.min(2))
-            else:
-                sep = sep | ((pa.max(2) < pb.min(2)) | (pb.max(2) < pa.min(2))).any(1, keepdims=True) if False else sep
-            yield (pa.max(2) < pb.min(2)) | (pb.max(2) < pa.min(2))
+    def separated_on_normals_of(P, A, B):
+        """[m] bool: some edge normal of polygon batch P separates A from B (float64)."""
+        e = np.roll(P, -1, axis=1) - P
+        nrm = np.stack([e[..., 1], -e[..., 0]], -1)
+        pa = np.einsum("nik,njk->nij", nrm, A); pb = np.einsum("nik,njk->nij", nrm, B)
+        return ((pa.max(2) < pb.min(2)) | (pb.max(2) < pa.min(2))).any(1)
     m = 200_000
     for i in range(pp.size):
         zz = rng.standard_normal((3, m))
@@ -110,8 +106,7 @@ def test_polygon_fused_sharding_and_float64_probability(ctx, dev, satmc):
         Ow = np.stack([c * O[None, :, 0] - s * O[None, :, 1] + (zz[0] * pp["sd_x"][i])[:, None],
                        s * O[None, :, 0] + c * O[None, :, 1] + (zz[1] * pp["sd_y"][i])[:, None]], 2)
         A = np.broadcast_to(Rw, (m,) + Rw.shape)
-        seps = list(sat64(A, Ow))
-        hit = ~(seps[0].any(1) | seps[1].any(1))
+        hit = ~(separated_on_normals_of(A, A, Ow) | separated_on_normals_of(Ow, A, Ow))
         p_ref = hit.mean(); p = whole[i] / n
         pm = (p + p_ref) / 2
         assert abs(p - p_ref) < 4.9 * math.sqrt(pm * (1 - pm) * (1 / n + 1 / m)) + 1e-9, (i, p, p_ref)

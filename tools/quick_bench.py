@@ -76,6 +76,17 @@ def main():
         gb = ndof * 4 * npairs * n / 1e9
         print(f"streamed private ndof={ndof} {npairs}x{n}: best {best:.3f} ms {npairs * n / best / 1e6:.2f} Gtests/s  {gb / best * 1e3:.1f} GB/s")
         del z
+    if "--poly" in sys.argv:
+        rng = np.random.default_rng(0)
+        base = wl.dataset_pairs(100_000, 3)
+        def rect(w, h): return np.array([[-w / 2, -h / 2], [w / 2, -h / 2], [w / 2, h / 2], [-w / 2, h / 2]], np.float32)
+        def reg(k, r): a = 2 * np.pi * np.arange(k) / k; return np.stack([r * np.cos(a), r * np.sin(a)], 1).astype(np.float32)
+        for name, robots, obstacles in (("4x4 (rectangles)", [rect(4.07, 1.74)] * base.size, [rect(p["ow"], p["oh"]) for p in base]),
+                                        ("8x8 (octagons)", [reg(8, 2.0)] * base.size, [reg(8, 0.3 * (p["ow"] + p["oh"])) for p in base])):
+            pp = satmc.make_poly_pairs(robots, obstacles, base["rx"], base["ry"], base["rtheta"], base["sd_x"], base["sd_y"], base["sd_theta"])
+            d_pp = torch.from_numpy(pp.view(np.uint8).view(np.float32)).cuda(); d_h = torch.zeros(pp.size, dtype=torch.int64, device="cuda")
+            best, med = time_call(lambda: ctx.count_fused_polygons(d_pp, pp.size, 10_000, 7, d_h), reps=3)
+            print(f"fused polygons {name:18s} 1e5x1e4: best {best:.3f} ms {pp.size * 1e4 / best / 1e6:.2f} Gtests/s p={d_h.sum().item() / (pp.size * 1e4):.4f}")
     if "--ref" in sys.argv:
         from oracle.binding import RefGpu
         ref = RefGpu()
