@@ -1,0 +1,708 @@
+// satmc_kernels.cuh -- the device side of libsatmc: counting kernels for the Monte Carlo SAT path (sm_100a).
+//
+// Work decomposition: a work item is (pair, sample chunk); one warp owns one
+// item at a time (grid-stride over items), its 32 lanes stride over the samples of the chunk, each
+// lane keeps a private hit counter, and the item ends with one REDUX warp reduction and one store
+// or one atomic.  When every warp of a block works on the same pair the warp sums are combined in
+// shared memory first and the block issues a single 64-bit atomic.
+//
+// The reference does the opposite (one thread = one pair, serial over samples, RNG state in global
+// memory, ztest.cu:122-155), which starves the GPU whenever pairs < resident threads.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/satmc.h"
+#include "satmc_geom.cuh"
+#include "satmc_poly.cuh"
+#include "satmc_sampler.cuh"
+
+namespace satmc {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+// resident blocks per SM the register allocator aims for: the fused loop is FMA-pipe bound and wants
+// registers (2 x 256 threads at 128 regs), the streamed loop is latency bound and wants warps
+// (measured on B200: fused 254 vs 246 Gtests/s, streamed 3-DoF 3.8 vs 4.9 TB/s for 2 vs 4 blocks)
+#ifndef SATMC_MIN_BLOCKS_FUSED
+#define SATMC_MIN_BLOCKS_FUSED 2
+#endif
+#ifndef SATMC_MIN_BLOCKS_STREAMED
+#define SATMC_MIN_BLOCKS_STREAMED 4
+#endif
+// bulk-tensor streamed kernel (measured: 3-DoF 5.58 / 5.73 / 5.26 TB/s, 5-DoF 6.62 / 5.88 / 5.74 TB/s at 2 / 3 / 4 blocks)
+#ifndef SATMC_MIN_BLOCKS_TMA3
+#define SATMC_MIN_BLOCKS_TMA3 3
+#endif
+#ifndef SATMC_MIN_BLOCKS_TMA5
+#define SATMC_MIN_BLOCKS_TMA5 2
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// pair sources
+// ---------------------------------------------------------------------------------------------
+struct DirectSrc {
+    const satmc_pair* pairs;
+    __device__ __forceinline__ uint64_t element(uint64_t slot) const { return slot; }
+    __device__ __forceinline__ void load(uint64_t i, float v[12]) const {
+        const float4* p = reinterpret_cast<const float4*>(pairs + i);   // 48 B, 16-B aligned
+        const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y;
+        v[6] = b.z; v[7] = b.w; v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+    }
+};
+
+// The reference's indirect layout (ztest.cu:135-140): per live pair a position and two float indices
+// into the pose and std-dev tables; the robot is create_rect(robot_w, robot_h).
+struct IndirectSrc {
+    const float* robot_base; const float* poses; const float* std_devs;
+    const float* pose_idxs; const float* std_dev_idxs; const float* positions;
+    uint32_t n_poses, n_std;
+    const int* live;               // optional: slot -> pair id (device-side work list of unfinished pairs)
+    __device__ __forceinline__ uint64_t element(uint64_t slot) const { return live ? (uint64_t)__ldg(live + slot) : slot; }
+    __device__ __forceinline__ void load(uint64_t i, float v[12]) const {
+        uint32_t pi = (uint32_t)(int)__ldg(pose_idxs + i);
+        uint32_t si = (uint32_t)(int)__ldg(std_dev_idxs + i);
+        pi = pi < n_poses ? pi : n_poses - 1;          // the reference would read out of bounds
+        si = si < n_std ? si : n_std - 1;
+        v[0] = __ldg(positions + 2 * i); v[1] = __ldg(positions + 2 * i + 1);
+        v[2] = __ldg(poses + 3 * (size_t)pi + 2);
+        v[3] = 2.0f * __ldg(robot_base + 2);           // create_rect: r[2] = w/2, r[5] = h/2 (exact)
+        v[4] = 2.0f * __ldg(robot_base + 5);
+        v[5] = __ldg(poses + 3 * (size_t)pi); v[6] = __ldg(poses + 3 * (size_t)pi + 1);
+#pragma unroll
+        for (int k = 0; k < 5; k++) v[7 + k] = __ldg(std_devs + 5 * (size_t)si + k);
+    }
+};
+
+struct CountParams {
+    uint64_t n_pairs;
+    uint64_t n_samples;        // per pair
+    uint64_t sample_offset;    // fused: first sample index
+    uint64_t chunk;            // samples per work item (multiple of 128)
+    uint64_t n_items;          // n_pairs * n_chunks
+    uint32_t n_chunks;
+    uint32_t pair_id_offset;
+    uint32_t flags;            // SATMC_ACCUMULATE | SATMC_EXACT_ONLY
+    uint32_t block_uniform;    // all warps of a block share a pair -> block reduction
+    unsigned long long* hits;
+    unsigned long long* exact_evals;
+    // streamed
+    const float* z; uint64_t ldz; uint64_t z_pair_stride; int ndof; int vec_ok;
+    PhiloxKeys keys;           // fused: round keys, read straight from the constant bank
+};
+
+// Slow, general evaluation of the slots of one sample group selected by slot_mask (bit t = sample
+// 4g+t): used for the ragged ends of a chunk and whenever the hot loop meets a sample the screening
+// pass cannot decide.  The normals are regenerated from the counter, so the hot loop keeps nothing
+// alive for it.
+template <int D>
+__device__ __noinline__ unsigned fused_group_slow(const PairConst& P, const float* robot, uint64_t g, unsigned slot_mask,
+                                                  uint32_t pid, const PhiloxKeys& K, unsigned long long* exact_evals)
+{
+    float n[4 * D];
+    group_normals<D>((uint32_t)g, (uint32_t)(g >> 32), pid, K, n);
+    unsigned cnt = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        if (!(slot_mask & (1u << t))) continue;
+        const float z3 = (D == 5) ? n[D * t + 3] : 0.0f, z4 = (D == 5) ? n[D * t + 4] : 0.0f;
+        float hmin;
+        const float m = screen_gap<D>(P, n[D * t], n[D * t + 1], n[D * t + 2], z3, z4, hmin);
+        unsigned hit = __float_as_uint(m) >> 31;
+        if (!screen_decided<D>(P, m, hmin)) {
+            hit = (unsigned)exact_decide(robot, P.ow, P.oh, P.sd_x, P.sd_y, P.sd_t, P.sd_w, P.sd_h, n[D * t], n[D * t + 1],
+                                         n[D * t + 2], z3, z4);
+            if (exact_evals) atomicAdd(exact_evals, 1ull);
+        }
+        cnt += hit;
+    }
+    return cnt;
+}
+
+// hot path: all four samples of group g
+template <int D>
+__device__ __forceinline__ unsigned fused_group(const PairConst& P, const PairConst& Pcold, const float* robot, uint64_t g,
+                                                uint32_t pid, const PhiloxKeys& K, unsigned long long* exact_evals)
+{
+    float n[4 * D];
+    group_normals<D>((uint32_t)g, (uint32_t)(g >> 32), pid, K, n);
+    unsigned cnt = 0;
+    bool decided = true;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const float z3 = (D == 5) ? n[D * t + 3] : 0.0f, z4 = (D == 5) ? n[D * t + 4] : 0.0f;
+        float hmin;
+        const float m = screen_gap<D>(P, n[D * t], n[D * t + 1], n[D * t + 2], z3, z4, hmin);
+        cnt += __float_as_uint(m) >> 31;                            // m < 0 (m = -0 / NaN are undecided anyway)
+        decided = decided && screen_decided<D>(P, m, hmin);
+    }
+    if (!decided) cnt = fused_group_slow<D>(Pcold, robot, g, 0xFu, pid, K, exact_evals);   // rare: redo the group
+    return cnt;
+}
+
+// one sample of the streamed path (normals supplied)
+template <int NDOF>
+__device__ __noinline__ unsigned streamed_sample(const PairConst& P, const float* robot, float z0, float z1,
+                                                    float z2, float z3, float z4, unsigned long long* exact_evals)
+{
+    float hmin;
+    const float m = screen_gap<NDOF>(P, z0, z1, z2, z3, z4, hmin);
+    unsigned hit = __float_as_uint(m) >> 31;
+    // the screening bound assumes |z| <= SATMC_Z_BOUND; "<=" is false for NaN, so NaN/Inf go exact
+    bool ok = screen_decided<NDOF>(P, m, hmin);
+    ok = ok && (fabsf(z0) <= SATMC_Z_BOUND) && (fabsf(z1) <= SATMC_Z_BOUND) && (fabsf(z2) <= SATMC_Z_BOUND);
+    if (NDOF == 5) ok = ok && (fabsf(z3) <= SATMC_Z_BOUND) && (fabsf(z4) <= SATMC_Z_BOUND);
+    if (!ok) {
+        hit = (unsigned)exact_decide(robot, P.ow, P.oh, P.sd_x, P.sd_y, P.sd_t, P.sd_w, P.sd_h, z0, z1, z2, z3, z4);
+        if (exact_evals) atomicAdd(exact_evals, 1ull);
+    }
+    return hit;
+}
+
+// samples [b, e) (absolute indices) of one pair: full groups go through the hot loop, the at most two
+// ragged groups at the ends through the slow path on lanes 0 and 1
+// P lives in registers for the hot loop; Pcold is the same data in shared memory, handed to the out-of-line
+// cold functions so that P's address is never taken (otherwise the compiler homes P on the local stack).
+template <int D>
+__device__ __forceinline__ unsigned fused_chunk(const PairConst& P, const PairConst& Pcold, const float* robot, uint64_t b,
+                                                uint64_t e, uint32_t pid, const PhiloxKeys& K, int lane,
+                                                unsigned long long* exact_evals)
+{
+    unsigned cnt = 0;
+    const uint64_t g_lo = (b + 3) >> 2, g_hi = e >> 2;
+    if (g_hi < g_lo) {                                              // whole range inside one group
+        if (lane == 0) {
+            const unsigned mask = (0xFu << (unsigned)(b & 3)) & (0xFu >> (4 - (unsigned)(e & 3))) & 0xFu;
+            cnt = fused_group_slow<D>(Pcold, robot, b >> 2, mask, pid, K, exact_evals);
+        }
+        return cnt;
+    }
+    for (uint64_t g = g_lo + (uint64_t)lane; g < g_hi; g += 32)
+        cnt += fused_group<D>(P, Pcold, robot, g, pid, K, exact_evals);
+    if (lane == 0 && (b & 3))
+        cnt += fused_group_slow<D>(Pcold, robot, b >> 2, (0xFu << (unsigned)(b & 3)) & 0xFu, pid, K, exact_evals);
+    if (lane == 1 && (e & 3))
+        cnt += fused_group_slow<D>(Pcold, robot, g_hi, 0xFu >> (4 - (unsigned)(e & 3)), pid, K, exact_evals);
+    return cnt;
+}
+
+// screening value of one streamed sample and whether it is decided (|z| guard included)
+template <int NDOF>
+__device__ __forceinline__ bool streamed_screen(const PairConst& P, float z0, float z1, float z2, float z3, float z4,
+                                                unsigned& hit)
+{
+    float hmin;
+    const float m = screen_gap<NDOF>(P, z0, z1, z2, z3, z4, hmin);
+    hit = __float_as_uint(m) >> 31;
+    bool ok = screen_decided<NDOF>(P, m, hmin);
+    ok = ok & (fabsf(z0) <= SATMC_Z_BOUND) & (fabsf(z1) <= SATMC_Z_BOUND) & (fabsf(z2) <= SATMC_Z_BOUND);
+    if (NDOF == 5) ok = ok & (fabsf(z3) <= SATMC_Z_BOUND) & (fabsf(z4) <= SATMC_Z_BOUND);
+    return ok;
+}
+
+// Cold path of the vector loop: re-read the four samples starting at z[i] (they are still in L1/L2) and decide
+// each with screening + exact fallback; the hot loop keeps nothing alive for it.
+template <int NDOF>
+__device__ __noinline__ unsigned streamed_quad_slow(const PairConst& P, const float* robot, const float* __restrict__ z,
+                                                    uint64_t ldz, uint64_t i, unsigned long long* exact_evals)
+{
+    unsigned cnt = 0;
+    for (int t = 0; t < 4; t++) {
+        const float z0 = z[i + t], z1 = z[ldz + i + t], z2 = z[2 * ldz + i + t];
+        const float z3 = (NDOF == 5) ? z[3 * ldz + i + t] : 0.0f, z4 = (NDOF == 5) ? z[4 * ldz + i + t] : 0.0f;
+        cnt += streamed_sample<NDOF>(P, robot, z0, z1, z2, z3, z4, exact_evals);
+    }
+    return cnt;
+}
+
+template <int NDOF>
+struct ZQuad { float4 a, b, c, d, e; };
+
+template <int NDOF>
+__device__ __forceinline__ void load_quad(ZQuad<NDOF>& q, const float* __restrict__ z, uint64_t ldz, uint64_t v)
+{
+    q.a = __ldg(reinterpret_cast<const float4*>(z) + v);
+    q.b = __ldg(reinterpret_cast<const float4*>(z + ldz) + v);
+    q.c = __ldg(reinterpret_cast<const float4*>(z + 2 * ldz) + v);
+    if (NDOF == 5) {
+        q.d = __ldg(reinterpret_cast<const float4*>(z + 3 * ldz) + v);
+        q.e = __ldg(reinterpret_cast<const float4*>(z + 4 * ldz) + v);
+    } else {
+        q.d = make_float4(0.f, 0.f, 0.f, 0.f); q.e = q.d;
+    }
+}
+
+template <int NDOF>
+__device__ __forceinline__ unsigned streamed_chunk(const PairConst& P, const PairConst& Pcold, const float* robot,
+                                                   const float* __restrict__ z, uint64_t ldz, uint64_t len, int vec_ok,
+                                                   int lane, unsigned long long* exact_evals)
+{
+    unsigned cnt = 0;
+    uint64_t done = 0;
+    if (vec_ok) {
+        // 4 samples per lane per trip from one LDG.128 per plane; the next trip's loads are issued before this
+        // trip's arithmetic (register double buffering) so that each warp keeps 2 x ndof x 512 B in flight
+        const uint64_t nvec = len / 4;
+        uint64_t v = (uint64_t)lane;
+        ZQuad<NDOF> cur, nxt;
+        if (v < nvec) load_quad<NDOF>(cur, z, ldz, v);
+        for (; v < nvec; v += 32) {
+            const uint64_t vn = v + 32;
+            if (vn < nvec) load_quad<NDOF>(nxt, z, ldz, vn);
+            unsigned h0, h1, h2, h3;
+            bool ok = streamed_screen<NDOF>(P, cur.a.x, cur.b.x, cur.c.x, cur.d.x, cur.e.x, h0);
+            ok = ok & streamed_screen<NDOF>(P, cur.a.y, cur.b.y, cur.c.y, cur.d.y, cur.e.y, h1);
+            ok = ok & streamed_screen<NDOF>(P, cur.a.z, cur.b.z, cur.c.z, cur.d.z, cur.e.z, h2);
+            ok = ok & streamed_screen<NDOF>(P, cur.a.w, cur.b.w, cur.c.w, cur.d.w, cur.e.w, h3);
+            unsigned c4 = h0 + h1 + h2 + h3;
+            if (!ok) c4 = streamed_quad_slow<NDOF>(Pcold, robot, z, ldz, 4 * v, exact_evals);   // rare: redo the four
+            cnt += c4;
+            cur = nxt;
+        }
+        done = nvec * 4;
+    }
+    for (uint64_t i = done + (uint64_t)lane; i < len; i += 32) {
+        const float z0 = __ldg(z + i), z1 = __ldg(z + ldz + i), z2 = __ldg(z + 2 * ldz + i);
+        float z3 = 0.f, z4 = 0.f;
+        if (NDOF == 5) { z3 = __ldg(z + 3 * ldz + i); z4 = __ldg(z + 4 * ldz + i); }
+        cnt += streamed_sample<NDOF>(Pcold, robot, z0, z1, z2, z3, z4, exact_evals);
+    }
+    return cnt;
+}
+
+template <class Src, bool STREAMED>
+__global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED : SATMC_MIN_BLOCKS_FUSED) k_count(const __grid_constant__ Src src, const __grid_constant__ CountParams p)
+{
+    __shared__ float s_robot[kWarps][8];
+    __shared__ PairConst s_pair[kWarps];
+    __shared__ unsigned s_part[kWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t)gridDim.x * kWarps;
+    // items are laid out pair-major; with block_uniform all 8 warps of a block walk the loop in step
+    for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < p.n_items; item += stride) {
+        const uint64_t pair = item / p.n_chunks;
+        const uint32_t chunk_id = (uint32_t)(item - pair * p.n_chunks);
+        float v[12];
+        const uint64_t elem = src.element(pair);                    // array index and Philox stream of this slot
+        src.load(elem, v);
+        PairConst P;
+        pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
+        if (p.flags & SATMC_EXACT_ONLY) { P.eps = CUDART_INF_F; P.eps_b = CUDART_INF_F; }
+        __syncwarp();
+        if (lane == 0) { exact_robot_corners(v[0], v[1], P.ca, P.sa, v[3], v[4], s_robot[warp]); s_pair[warp] = P; }
+        __syncwarp();
+        const PairConst& Pc = s_pair[warp];
+        const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
+        const uint64_t c_len = (c_begin + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - c_begin);
+        unsigned long long* ev = (p.flags & SATMC_EXACT_ONLY) ? nullptr : p.exact_evals;
+        unsigned cnt;
+        if (STREAMED) {
+            const float* z = p.z + pair * p.z_pair_stride + c_begin;
+            cnt = (p.ndof == 5) ? streamed_chunk<5>(P, Pc, s_robot[warp], z, p.ldz, c_len, p.vec_ok, lane, ev)
+                                : streamed_chunk<3>(P, Pc, s_robot[warp], z, p.ldz, c_len, p.vec_ok, lane, ev);
+        } else {
+            const uint32_t pid = p.pair_id_offset + (uint32_t)elem;
+            const uint64_t s_begin = p.sample_offset + c_begin;
+            const bool dof3 = (v[10] == 0.0f) && (v[11] == 0.0f);
+            cnt = dof3 ? fused_chunk<3>(P, Pc, s_robot[warp], s_begin, s_begin + c_len, pid, p.keys, lane, ev)
+                       : fused_chunk<5>(P, Pc, s_robot[warp], s_begin, s_begin + c_len, pid, p.keys, lane, ev);
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (p.block_uniform) {
+            if (lane == 0) s_part[warp] = cnt;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long t = 0;
+#pragma unroll
+                for (int w = 0; w < kWarps; w++) t += s_part[w];
+                atomicAdd(p.hits + pair, t);                       // one atomic per block
+            }
+            __syncthreads();
+        } else if (lane == 0) {
+            if (p.n_chunks == 1) {
+                if (p.flags & SATMC_ACCUMULATE) p.hits[pair] += cnt; else p.hits[pair] = cnt;
+            } else {
+                atomicAdd(p.hits + pair, (unsigned long long)cnt);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// streamed path, bulk-copy staged (the default when the sample bank is 16-byte aligned)
+//
+// The sample bank is described to the TMA unit as a 2-D tensor [ndof planes][ldz samples].  Each warp runs a
+// private 2-stage ring in shared memory: lane 0 issues ONE cp.async.bulk.tensor.2d (UTMALDG) for the next
+// tile of 128 samples x ndof planes, completion is signalled on an mbarrier with expect_tx, and the 32
+// lanes read their 4 samples per plane with one conflict-free LDS.128.  The bytes in flight live in shared
+// memory instead of registers (32 warps x 2 stages x ndof x 512 B per SM) and the hot loop has no LDG and
+// no address arithmetic.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTile = 128;            // samples per tile per plane = 32 lanes x float4
+constexpr int kStages = 2;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" :: "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(smem_addr(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_addr(bar)) : "memory");
+}
+
+template <int NDOF>
+__global__ void __launch_bounds__(kThreads, NDOF == 5 ? SATMC_MIN_BLOCKS_TMA5 : SATMC_MIN_BLOCKS_TMA3)
+k_count_streamed_tma(const __grid_constant__ DirectSrc src, const __grid_constant__ CountParams p,
+                     const __grid_constant__ CUtensorMap zmap)
+{
+    extern __shared__ __align__(128) float s_tiles[];                 // [kWarps][kStages][NDOF][kTile]
+    __shared__ __align__(8) uint64_t s_bar[kWarps][kStages];
+    __shared__ float s_robot[kWarps][8];
+    __shared__ PairConst s_pair[kWarps];
+    __shared__ unsigned s_part[kWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* my_tiles = s_tiles + (size_t)warp * kStages * NDOF * kTile;
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < kStages; st++) mbar_init(&s_bar[warp][st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t tiles_done = 0;                                          // running tile counter: stage and parity
+    const uint64_t stride = (uint64_t)gridDim.x * kWarps;
+    for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < p.n_items; item += stride) {
+        const uint64_t pair = item / p.n_chunks;
+        const uint32_t chunk_id = (uint32_t)(item - pair * p.n_chunks);
+        float v[12];
+        src.load(pair, v);
+        PairConst P;
+        pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
+        if (p.flags & SATMC_EXACT_ONLY) { P.eps = CUDART_INF_F; P.eps_b = CUDART_INF_F; }
+        __syncwarp();
+        if (lane == 0) { exact_robot_corners(v[0], v[1], P.ca, P.sa, v[3], v[4], s_robot[warp]); s_pair[warp] = P; }
+        __syncwarp();
+        const PairConst& Pc = s_pair[warp];
+        const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
+        const uint64_t c_len = (c_begin + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - c_begin);
+        unsigned long long* ev = (p.flags & SATMC_EXACT_ONLY) ? nullptr : p.exact_evals;
+        const float* z = p.z + pair * p.z_pair_stride + c_begin;
+        const uint32_t n_tiles = (uint32_t)(c_len / kTile);
+        const int x0 = (int)(pair * p.z_pair_stride + c_begin);       // tensor coordinate of the chunk (< 2^31, host-checked)
+        auto issue = [&](uint32_t t) {                                // lane 0 only
+            const uint32_t st = (tiles_done + t) % kStages;
+            mbar_expect_tx(&s_bar[warp][st], NDOF * kTile * 4);
+            tma_load_2d(my_tiles + (size_t)st * NDOF * kTile, &zmap, x0 + (int)(t * kTile), 0, &s_bar[warp][st]);
+        };
+        if (lane == 0)
+            for (uint32_t t = 0; t < n_tiles && t < (uint32_t)kStages; t++) issue(t);
+        unsigned cnt = 0;
+        for (uint32_t t = 0; t < n_tiles; t++) {
+            const uint32_t seq = tiles_done + t, st = seq % kStages;
+            mbar_wait(&s_bar[warp][st], (seq / kStages) & 1u);
+            const float4* tp = reinterpret_cast<const float4*>(my_tiles + (size_t)st * NDOF * kTile) + lane;
+            const float4 a = tp[0], b = tp[kTile / 4], c = tp[2 * (kTile / 4)];
+            float4 d = make_float4(0.f, 0.f, 0.f, 0.f), e = d;
+            if (NDOF == 5) { d = tp[3 * (kTile / 4)]; e = tp[4 * (kTile / 4)]; }
+            __syncwarp();                                             // every lane has its samples: the stage is free
+            if (lane == 0 && t + kStages < n_tiles) issue(t + kStages);   // __syncwarp ordered the reads before this write
+            unsigned h0, h1, h2, h3;
+            bool ok = streamed_screen<NDOF>(P, a.x, b.x, c.x, d.x, e.x, h0);
+            ok = ok & streamed_screen<NDOF>(P, a.y, b.y, c.y, d.y, e.y, h1);
+            ok = ok & streamed_screen<NDOF>(P, a.z, b.z, c.z, d.z, e.z, h2);
+            ok = ok & streamed_screen<NDOF>(P, a.w, b.w, c.w, d.w, e.w, h3);
+            unsigned c4 = h0 + h1 + h2 + h3;
+            if (!ok) c4 = streamed_quad_slow<NDOF>(Pc, s_robot[warp], z, p.ldz, (uint64_t)t * kTile + 4 * lane, ev);
+            cnt += c4;
+        }
+        tiles_done += n_tiles;
+        for (uint64_t i = (uint64_t)n_tiles * kTile + (uint64_t)lane; i < c_len; i += 32) {      // ragged tail
+            const float z0 = __ldg(z + i), z1 = __ldg(z + p.ldz + i), z2 = __ldg(z + 2 * p.ldz + i);
+            float z3 = 0.f, z4 = 0.f;
+            if (NDOF == 5) { z3 = __ldg(z + 3 * p.ldz + i); z4 = __ldg(z + 4 * p.ldz + i); }
+            cnt += streamed_sample<NDOF>(Pc, s_robot[warp], z0, z1, z2, z3, z4, ev);
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (p.block_uniform) {
+            if (lane == 0) s_part[warp] = cnt;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long tsum = 0;
+#pragma unroll
+                for (int w = 0; w < kWarps; w++) tsum += s_part[w];
+                atomicAdd(p.hits + pair, tsum);
+            }
+            __syncthreads();
+        } else if (lane == 0) {
+            if (p.n_chunks == 1) {
+                if (p.flags & SATMC_ACCUMULATE) p.hits[pair] += cnt; else p.hits[pair] = cnt;
+            } else {
+                atomicAdd(p.hits + pair, (unsigned long long)cnt);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// general convex polygons: same work decomposition, sampler and counting as k_count;
+// every sample is evaluated with the exact polygon SAT of satmc_poly.cuh (no screening pass yet)
+// ---------------------------------------------------------------------------------------------
+template <bool STREAMED>
+__global__ void __launch_bounds__(kThreads, 2) k_count_poly(const float* __restrict__ pairs, const __grid_constant__ CountParams p)
+{
+    __shared__ PolyPairShared s_poly[kWarps];
+    __shared__ unsigned s_part[kWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t)gridDim.x * kWarps;
+    for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < p.n_items; item += stride) {
+        const uint64_t pair = item / p.n_chunks;
+        const uint32_t chunk_id = (uint32_t)(item - pair * p.n_chunks);
+        __syncwarp();
+        if (lane == 0) poly_prologue(s_poly[warp], pairs + pair * 40);          // 160-byte descriptors
+        __syncwarp();
+        const PolyPairShared& S = s_poly[warp];
+        const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
+        const uint64_t c_len = (c_begin + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - c_begin);
+        unsigned cnt = 0;
+        if (STREAMED) {
+            const float* z = p.z + pair * p.z_pair_stride + c_begin;
+            for (uint64_t i = (uint64_t)lane; i < c_len; i += 32)
+                cnt += poly_collide(S, __ldg(z + i), __ldg(z + p.ldz + i), __ldg(z + 2 * p.ldz + i));
+        } else {
+            const uint32_t pid = p.pair_id_offset + (uint32_t)pair;
+            const uint64_t b = p.sample_offset + c_begin, e = b + c_len;
+            for (uint64_t g = (b >> 2) + (uint64_t)lane; 4 * g < e; g += 32) {    // 4-sample groups, ragged ends masked
+                float n[12];
+                group_normals<3>((uint32_t)g, (uint32_t)(g >> 32), pid, p.keys, n);
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const uint64_t sidx = 4 * g + t;
+                    if (sidx >= b && sidx < e) cnt += poly_collide(S, n[3 * t], n[3 * t + 1], n[3 * t + 2]);
+                }
+            }
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (p.block_uniform) {
+            if (lane == 0) s_part[warp] = cnt;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long t = 0;
+#pragma unroll
+                for (int w = 0; w < kWarps; w++) t += s_part[w];
+                atomicAdd(p.hits + pair, t);
+            }
+            __syncthreads();
+        } else if (lane == 0) {
+            if (p.n_chunks == 1) {
+                if (p.flags & SATMC_ACCUMULATE) p.hits[pair] += cnt; else p.hits[pair] = cnt;
+            } else {
+                atomicAdd(p.hits + pair, (unsigned long long)cnt);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_decide(satmc_pair const* pair, const float* __restrict__ z, uint64_t ldz, int ndof, uint64_t n,
+                         uint8_t* out, uint32_t flags, unsigned long long* exact_evals)
+{
+    __shared__ float s_robot[8];
+    float v[12];
+    DirectSrc src{pair};
+    src.load(0, v);
+    PairConst P;
+    pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
+    if (flags & SATMC_EXACT_ONLY) { P.eps = CUDART_INF_F; P.eps_b = CUDART_INF_F; }
+    if (threadIdx.x == 0) exact_robot_corners(v[0], v[1], P.ca, P.sa, v[3], v[4], s_robot);
+    __syncthreads();
+    unsigned long long* ev = (flags & SATMC_EXACT_ONLY) ? nullptr : exact_evals;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float z0 = z[i], z1 = z[ldz + i], z2 = z[2 * ldz + i];
+        unsigned h;
+        if (ndof == 5) h = streamed_sample<5>(P, s_robot, z0, z1, z2, z[3 * ldz + i], z[4 * ldz + i], ev);
+        else           h = streamed_sample<3>(P, s_robot, z0, z1, z2, 0.f, 0.f, ev);
+        out[i] = (uint8_t)h;
+    }
+}
+
+// normals of samples [offset, offset+n) of stream pid, D planes (D = 3 or 5); one thread per group
+// diagnostics: the screening value m and the threshold it is compared with, per streamed sample of one pair
+__global__ void k_screen_debug(satmc_pair const* pair, const float* __restrict__ z, uint64_t ldz, int ndof, uint64_t n,
+                               float* m_out, float* eps_out)
+{
+    float v[12];
+    DirectSrc src{pair};
+    src.load(0, v);
+    PairConst P;
+    pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        float hmin;
+        if (ndof == 5) {
+            m_out[i] = screen_gap<5>(P, z[i], z[ldz + i], z[2 * ldz + i], z[3 * ldz + i], z[4 * ldz + i], hmin);
+            eps_out[i] = (hmin > 0.0f) ? P.eps_a + P.eps_b / hmin : CUDART_INF_F;
+        } else {
+            m_out[i] = screen_gap<3>(P, z[i], z[ldz + i], z[2 * ldz + i], 0.f, 0.f, hmin);
+            eps_out[i] = P.eps;
+        }
+    }
+}
+
+template <int D>
+__global__ void k_fused_normals(const __grid_constant__ PhiloxKeys K, uint32_t pid, uint64_t offset, uint64_t n, float* z, uint64_t ldz)
+{
+    const uint64_t g0 = offset >> 2, g1 = (offset + n + 3) >> 2;
+    for (uint64_t g = g0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < g1; g += (uint64_t)gridDim.x * blockDim.x) {
+        float nn[4 * D];
+        group_normals<D>((uint32_t)g, (uint32_t)(g >> 32), pid, K, nn);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const uint64_t s = 4 * g + t;
+            if (s < offset || s >= offset + n) continue;
+#pragma unroll
+            for (int k = 0; k < D; k++) z[k * ldz + (s - offset)] = nn[D * t + k];
+        }
+    }
+}
+
+__global__ void k_philox(const uint32_t* ctr, uint64_t n, const __grid_constant__ PhiloxKeys K, uint32_t* out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[4];
+    philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], K, w);
+    out[4 * i] = w[0]; out[4 * i + 1] = w[1]; out[4 * i + 2] = w[2]; out[4 * i + 3] = w[3];
+}
+
+__global__ void k_sat_corners(const float* __restrict__ r1, const float* __restrict__ r2, uint64_t n, uint8_t* out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a[8], b[8];
+    const float4* pa = reinterpret_cast<const float4*>(r1 + 8 * i);
+    const float4* pb = reinterpret_cast<const float4*>(r2 + 8 * i);
+    const float4 a0 = __ldg(pa), a1 = __ldg(pa + 1), b0 = __ldg(pb), b1 = __ldg(pb + 1);
+    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+    out[i] = (uint8_t)exact_convex_collide(a, b);
+}
+
+// calcSlack / getBin / done flag of the reference kernel tail (ztest.cu:156-165, utils.cu:186-207).
+// k*k is formed in 64 bits (the reference's int32 product wraps for k > 46340); bins are read in bounds.
+__device__ __forceinline__ float calc_slack(int n, int k)
+{
+    const float z = 1.96;
+    const float alpha = 0.025;
+    if (k == n || k == 0) return (float)(log(1.0 / alpha) / n);
+    const float kk = (float)((long long)k * (long long)k);
+    return z / n * sqrtf((float)k - kk / (float)n);
+}
+
+__global__ void k_ztest_tail(const unsigned long long* __restrict__ hits, float* cps, const float* __restrict__ bins,
+                             const float* __restrict__ bin_acc, int n_bins, int* done, int n_samples, int num_left,
+                             const int* __restrict__ live)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= num_left) return;
+    const int e = live ? live[g] : g;
+    const int k = (int)cps[e] + (int)hits[g];
+    const float slack = calc_slack(n_samples, k);
+    const float p = (float)k / (float)n_samples;
+    int bin = 0;
+    for (int i = 0; i + 1 < n_bins; i++)
+        if (p >= bins[i] && p <= bins[i + 1]) bin = i;
+    done[e] = (slack <= bin_acc[bin]) ? 1 : 0;
+    cps[e] = (float)k;
+}
+
+// ---- adaptive scheduler (replaces thrust::count + sort_by_key + tail copies, ztest.cu:359-371) ----
+__global__ void k_iota(int* a, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
+}
+
+// Splits the live list: finished pairs get their probability written in place (count / n_samples, the
+// arithmetic of write_collision_probability utils.cu:210-215) and leave the list, the rest are appended
+// to live_out.  Warp-aggregated append: one atomic per warp.
+__global__ void k_compact_live(const int* __restrict__ live_in, int num_left, const int* __restrict__ done,
+                               const float* __restrict__ counts, int n_samples, float* cp_out, int* n_samples_out,
+                               int* live_out, int* n_out, int finalize_all)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < num_left;
+    int e = 0; bool keep = false;
+    if (valid) {
+        e = live_in[i];
+        const bool fin = finalize_all || done[e] != 0;
+        if (fin) {
+            cp_out[e] = counts[e] / (float)n_samples;
+            if (n_samples_out) n_samples_out[e] = n_samples;
+        }
+        keep = !fin;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(n_out, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (keep) live_out[base + __popc(m & ((1u << lane) - 1u))] = e;
+}
+
+// iteration-0 draw of generate_dataset (generate_dataset.cu:207-219): pose index, std-dev index and a
+// robot position on the ring prior around the obstacle.  Philox stream = stream_id_offset + g, counter
+// block 0xffffffff (disjoint from the sample groups).
+__global__ void k_sample_positions(const __grid_constant__ PhiloxKeys K, const float* __restrict__ poses, uint32_t n_poses,
+                                   const float* __restrict__ std_devs, uint32_t n_std, int n, float r_offset, float spread,
+                                   uint32_t stream_id_offset, float* positions, float* pose_idxs, float* std_dev_idxs)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    uint32_t w[4], w2[4];
+    philox4x32_10(0xffffffffu, 0xffffffffu, stream_id_offset + (uint32_t)g, 0u, K, w);
+    philox4x32_10(0xffffffffu, 0xffffffffu, stream_id_offset + (uint32_t)g, 1u, K, w2);
+    const uint32_t pi = w[0] % n_poses, si = w[1] % n_std;                    // curand() % n   (:208-209)
+    const float pw = poses[3 * (size_t)pi], ph = poses[3 * (size_t)pi + 1];
+    const float sx = std_devs[5 * (size_t)si], sy = std_devs[5 * (size_t)si + 1];
+    const float uni = ((float)(w[2] >> 8) + 1.0f) * 5.9604645e-8f;            // curand_uniform: (0, 1]   (:213)
+    const float theta = (float)(uni * 2 * 3.14159265358979323846);
+    float nz, unused;
+    bm_pair(w2[0], w2[1], nz, unused);                                        // curand_normal            (:214)
+    const float shift = nz * ((sy + sx) / 2) * spread;
+    positions[2 * (size_t)g]     = (float)(cosf(theta) * ((pw / 2 + r_offset + 2.35 + sx) + shift));   // (:215)
+    positions[2 * (size_t)g + 1] = (float)(sinf(theta) * ((ph / 2 + r_offset + 2.35 + sy) + shift));   // (:216)
+    pose_idxs[g] = (float)pi;
+    std_dev_idxs[g] = (float)si;
+}
+
+__global__ void k_write_cp(float* counts, int n_done, int n_samples)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n_done) counts[g] = counts[g] / (float)n_samples;
+}
+
+__global__ void k_hits_to_cp(const unsigned long long* __restrict__ hits, uint64_t n, uint64_t n_samples, float* cp)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cp[i] = (float)hits[i] / (float)n_samples;
+}
+
+}  // namespace satmc
