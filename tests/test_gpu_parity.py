@@ -109,6 +109,27 @@ def test_streamed_counts_equal_reference_kernel(ctx, dev, refgpu, workloads):
     np.testing.assert_array_equal(got.astype(np.int64), cps.astype(np.int64))
 
 
+def test_cuda_path_on_committed_golden_fixtures(ctx, dev, satmc):
+    """The CUDA path on the committed golden vectors (tests/golden, produced by the compiled reference on a B200):
+    SAT decisions on explicit corners and the reference kernel's hit counts on the normals it drew."""
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gdir, "ref_convex_collide.npz"))
+    n = g["r1"].shape[0]
+    d_out = dev.zeros(n, np.uint8)
+    ctx.sat_corners(dev.put(g["r1"].ravel()), dev.put(g["r2"].ravel()), n, d_out)
+    np.testing.assert_array_equal(dev.get(d_out), g["collide"].astype(np.uint8))
+    g = np.load(os.path.join(gdir, "ref_mc_kernel.npz"))
+    pi, si = g["pose_idxs"].astype(int), g["sd_idxs"].astype(int)
+    rb = g["robot_base"]
+    pairs = satmc.pairs_from_columns(g["positions"][:, 0], g["positions"][:, 1], g["poses"][pi, 2], g["poses"][pi, 0], g["poses"][pi, 1],
+                                     g["std_devs"][si, 0], g["std_devs"][si, 1], g["std_devs"][si, 2], g["std_devs"][si, 3],
+                                     g["std_devs"][si, 4], rw=2 * rb[2], rh=2 * rb[5])
+    nb = int(g["n_batch"])
+    got = streamed(ctx, dev, pairs, g["z"], n=nb, z_pair_stride=nb).astype(np.int64)
+    np.testing.assert_array_equal(got, g["cps_out"].astype(np.int64) - g["cps_in"].astype(np.int64))
+
+
 # ---- many pairs, ragged sizes, both load paths ---------------------------------------------------
 @pytest.mark.parametrize("n", [1, 31, 33, 127, 129, 1000, 4097])
 @pytest.mark.parametrize("ndof", [3, 5])
