@@ -245,13 +245,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                        # samples every 50 ms through warm-up, the timed region and the e2e loop
     for s in range(args.warmup):
         flush.fill_(s & 0xff)
         step(s)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = ctx.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
@@ -264,7 +264,6 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     launches = ctx.launch_count - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    clocks = sampler.stop() if rank == 0 else None
     hits_total = int(d_hits.sum().item())
 
     # e2e: host buffers through the C ABI (pinned H2D + kernel + D2H inside the timed region)
@@ -281,6 +280,7 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_kernel_ms = ctx.last_kernel_ms()
+    clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([dev_ms, e2e_s * 1e3, t_wall * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
