@@ -4,7 +4,7 @@
 // (1000 samples per iteration up to 20 000, then 100 000, :281-286) and write
 // <data_out>/<start + b>.npy ([N,5] = (x, y, cp, var_idx, pose_idx)), start = the number of numbered
 // files already in data_out (:157).  Tables and meta are read from data_out, as upstream (:162-166).
-// Flags as upstream (:44-56) plus --seed / --device; rows are written in input order and then shuffled
+// Flags as upstream (:44-56) plus --seed / --device / --gpus; rows are written in input order and then shuffled
 // with std::default_random_engine(0) when --shuffle is true (:346-349).
 // Differences from upstream: every batch file may have its own number of rows (upstream sizes all
 // buffers from 0.npy, :164,174); upstream's seed is glibc's first rand() (srand commented out, :249).
@@ -29,7 +29,7 @@ struct Arguments {
     float robot_width = 4.07f, robot_height = 1.74f;
     bool shuffle = true;
     long long seed = -1;
-    int device = 0;
+    int device = 0, gpus = 1;
 };
 
 static Arguments parse_args(int argc, char** argv) {
@@ -44,7 +44,8 @@ static Arguments parse_args(int argc, char** argv) {
      .add("robot_height", Kind::Float, "robot height", 'h')
      .add("shuffle", Kind::Bool, "whether or not to shuffle data")
      .add("seed", Kind::Int, "RNG seed (default: 1804289383, glibc's first rand(), as upstream)")
-     .add("device", Kind::Int, "CUDA device index");
+     .add("device", Kind::Int, "CUDA device index (first device when --gpus > 1)")
+     .add("gpus", Kind::Int, "number of GPUs to shard the rows of each file over");
     p.parse(argc, argv);
     if (p.count("help")) { p.print_help(std::cout); std::cout << "\n"; exit(1); }
     if (p.count("data_in")) a.data_in = p.str("data_in");
@@ -55,6 +56,7 @@ static Arguments parse_args(int argc, char** argv) {
     if (p.count("shuffle")) a.shuffle = p.boolean("shuffle");
     if (p.count("seed")) a.seed = p.integer("seed");
     if (p.count("device")) a.device = p.integer("device");
+    if (p.count("gpus")) a.gpus = p.integer("gpus");
     return a;
 }
 
@@ -89,8 +91,8 @@ int main(int argc, char* argv[]) try {
     std::cout << "num poses: " << poses.size() << std::endl;
     std::cout << "num variances: " << variances.size() << std::endl;
 
-    Context ctx(args.device);
-    MonteCarlo mc(ctx, args.robot_width, args.robot_height, poses, to_std_devs(variances), accuracy_bins, bin_accuracy);
+    ShardedMonteCarlo mc(args.device, args.gpus, args.robot_width, args.robot_height, poses, to_std_devs(variances), accuracy_bins,
+                         bin_accuracy);
     const uint64_t seed = args.seed >= 0 ? (uint64_t)args.seed : 1804289383ull;
     auto begin = std::chrono::steady_clock::now();
     std::cout << "Begin computation..." << std::endl;
@@ -105,10 +107,9 @@ int main(int argc, char* argv[]) try {
         for (int i = 0; i < n; i++) {                                                 // :262-268
             pos[2 * i] = rows[i].x; pos[2 * i + 1] = rows[i].y; var_idx[i] = rows[i].var_idx; pose_idx[i] = rows[i].pose_idx;
         }
-        DeviceArray<float> d_pos(ctx, pos), d_pose_idx(ctx, pose_idx), d_var_idx(ctx, var_idx), d_cp(ctx, (size_t)n);
-        mc.run(d_pos, d_pose_idx, d_var_idx, n, Schedule::dataset(args.max_samples), seed, (uint32_t)(stream & 0xffffffffu), d_cp);
+        std::vector<float> cp = mc.run_rows(pos, pose_idx, var_idx, Schedule::dataset(args.max_samples), seed,
+                                            (uint32_t)(stream & 0xffffffffu));
         stream += (uint64_t)n;
-        std::vector<float> cp = d_cp.to_host();
         std::vector<PoseCPVarAndPoseIdx> dataset(n);
         for (int j = 0; j < n; j++) dataset[j] = {rows[j].x, rows[j].y, cp[j], rows[j].var_idx, rows[j].pose_idx};   // :337-344
         if (args.shuffle) std::shuffle(dataset.begin(), dataset.end(), std::default_random_engine(0));               // :346-349

@@ -3,8 +3,10 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/satmc.h"
@@ -126,6 +128,69 @@ private:
     uint32_t n_poses_, n_std_;
     int n_bins_;
     DeviceArray<float> d_robot_, d_poses_, d_sds_, d_bins_, d_acc_;
+};
+
+// The tables resident on `gpus` devices starting at `first_device` (one context per GPU, created once) and the
+// adaptive z-test over n host-side rows sharded across them: one host thread per GPU, contiguous row ranges.  Row i
+// always draws Philox stream stream_offset + i, so cp[] does not depend on the number of GPUs.
+class ShardedMonteCarlo {
+public:
+    ShardedMonteCarlo(int first_device, int gpus, float robot_w, float robot_h, const std::vector<Pose>& poses,
+                      const std::vector<StdDev>& sds, const std::vector<float>& accuracy_bins, const std::vector<float>& bin_accuracy) {
+        if (gpus < 1) gpus = 1;
+        for (int w = 0; w < gpus; w++) {
+            ctx_.emplace_back(new Context(first_device + w));
+            mc_.emplace_back(new MonteCarlo(*ctx_.back(), robot_w, robot_h, poses, sds, accuracy_bins, bin_accuracy));
+        }
+    }
+    ~ShardedMonteCarlo() {
+        for (MonteCarlo* m : mc_) delete m;
+        for (Context* c : ctx_) delete c;
+    }
+    ShardedMonteCarlo(const ShardedMonteCarlo&) = delete;
+    ShardedMonteCarlo& operator=(const ShardedMonteCarlo&) = delete;
+
+    std::vector<float> run_rows(const std::vector<float>& pos, const std::vector<float>& pose_idx, const std::vector<float>& var_idx,
+                                const Schedule& schedule, uint64_t seed, uint32_t stream_offset, int* iterations = nullptr,
+                                long long* samples = nullptr) {
+        const size_t n = pose_idx.size();
+        const size_t gpus = ctx_.size();
+        std::vector<float> cp(n);
+        std::mutex m;
+        std::string failure;
+        int max_iter = 0; long long total = 0;
+        auto worker = [&](size_t w) {
+            try {
+                const size_t lo = n * w / gpus, hi = n * (w + 1) / gpus;
+                if (hi == lo) return;
+                Context& ctx = *ctx_[w];
+                const size_t k = hi - lo;
+                DeviceArray<float> d_pos(ctx, 2 * k), d_pi(ctx, k), d_vi(ctx, k), d_cp(ctx, k);
+                d_pos.upload(pos.data() + 2 * lo, 2 * k); d_pi.upload(pose_idx.data() + lo, k); d_vi.upload(var_idx.data() + lo, k);
+                int it = 0; long long smp = 0;
+                mc_[w]->run(d_pos, d_pi, d_vi, (int)k, schedule, seed, stream_offset + (uint32_t)lo, d_cp, &it, &smp);
+                d_cp.download(cp.data() + lo, k);
+                std::lock_guard<std::mutex> lock(m);
+                if (it > max_iter) max_iter = it;
+                total += smp;
+            } catch (const std::exception& e) {
+                std::lock_guard<std::mutex> lock(m);
+                if (failure.empty()) failure = std::string("GPU shard ") + std::to_string(w) + ": " + e.what();
+            }
+        };
+        std::vector<std::thread> threads;
+        for (size_t w = 1; w < gpus; w++) threads.emplace_back(worker, w);
+        worker(0);
+        for (std::thread& t : threads) t.join();
+        if (!failure.empty()) throw Error(SATMC_ERR_CUDA, failure);
+        if (iterations) *iterations = max_iter;
+        if (samples) *samples = total;
+        return cp;
+    }
+
+private:
+    std::vector<Context*> ctx_;
+    std::vector<MonteCarlo*> mc_;
 };
 
 }  // namespace satmc_host

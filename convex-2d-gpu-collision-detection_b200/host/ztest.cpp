@@ -2,7 +2,7 @@
 // <data_dir>/poses.npy, variances.npy, meta/*.npy and an [N,4] file of (x, y, var_idx, pose_idx) rows,
 // estimates the collision probability of every row with the adaptive z-test loop (10 000 samples per
 // iteration, ztest.cu:332) and writes [N,5] = (x, y, cp, var_idx, pose_idx) or, with --cps_only 1, [N] cp.
-// Flags as upstream (ztest.cu:49-63) plus --seed / --device.
+// Flags as upstream (ztest.cu:49-63) plus --seed / --device / --gpus (rows sharded over GPUs; same output for any count).
 // Upstream quirks kept in effect, not in mechanism: the output is in input order -- upstream's shuffle
 // branches are inverted (ztest.cu:408-414 shuffle the array that is not written), so --shuffle never
 // changes the file; --meta_dir only suppresses writing the default meta files, the bins are always read
@@ -26,7 +26,7 @@ struct Arguments {
     float robot_width = 4.07f, robot_height = 1.74f;
     bool shuffle = true, cps_only = false;
     long long seed = -1;
-    int device = 0;
+    int device = 0, gpus = 1;
 };
 
 static Arguments parse_args(int argc, char** argv) {
@@ -44,7 +44,8 @@ static Arguments parse_args(int argc, char** argv) {
      .add("cps_only", Kind::Bool, "whether or not to only compute collision probabilities")
      .add("meta_dir", Kind::String, "path to meta folder containing accuracy_bins.npy and bin_accuracy.npy")
      .add("seed", Kind::Int, "RNG seed (default: from the clock, as upstream)")
-     .add("device", Kind::Int, "CUDA device index");
+     .add("device", Kind::Int, "CUDA device index (first device when --gpus > 1)")
+     .add("gpus", Kind::Int, "number of GPUs to shard the rows over");
     p.parse(argc, argv);
     if (p.count("help")) { p.print_help(std::cout); std::cout << "\n"; exit(1); }
     if (p.count("data_dir")) a.data_dir = p.str("data_dir");
@@ -58,6 +59,7 @@ static Arguments parse_args(int argc, char** argv) {
     if (p.count("meta_dir")) a.meta_dir = p.str("meta_dir");
     if (p.count("seed")) a.seed = p.integer("seed");
     if (p.count("device")) a.device = p.integer("device");
+    if (p.count("gpus")) a.gpus = p.integer("gpus");
     return a;
 }
 
@@ -113,17 +115,15 @@ int main(int argc, char* argv[]) try {
     for (int i = 0; i < n; i++) {                                                     // ztest.cu:262-268
         pos[2 * i] = rows[i].x; pos[2 * i + 1] = rows[i].y; var_idx[i] = rows[i].var_idx; pose_idx[i] = rows[i].pose_idx;
     }
-    Context ctx(args.device);
-    MonteCarlo mc(ctx, args.robot_width, args.robot_height, poses, to_std_devs(variances), accuracy_bins, bin_accuracy);
-    DeviceArray<float> d_pos(ctx, pos), d_pose_idx(ctx, pose_idx), d_var_idx(ctx, var_idx), d_cp(ctx, (size_t)n);
     const uint64_t seed = args.seed >= 0 ? (uint64_t)args.seed : (uint64_t)std::time(nullptr);
 
     auto begin = std::chrono::steady_clock::now();
     std::cout << "Total number of configurations: " << n << std::endl;
     std::cout << "Begin computation..." << std::endl;
     int iterations = 0; long long samples = 0;
-    mc.run(d_pos, d_pose_idx, d_var_idx, n, Schedule::ztest(args.max_samples), seed, 0, d_cp, &iterations, &samples);
-    std::vector<float> cp = d_cp.to_host();
+    ShardedMonteCarlo mc(args.device, args.gpus, args.robot_width, args.robot_height, poses, to_std_devs(variances), accuracy_bins,
+                         bin_accuracy);
+    std::vector<float> cp = mc.run_rows(pos, pose_idx, var_idx, Schedule::ztest(args.max_samples), seed, 0, &iterations, &samples);
 
     if (args.cps_only) {
         npyio::save_f32(data_file_out.string(), {(size_t)n}, cp);                    // ztest.cu:418-420

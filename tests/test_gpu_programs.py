@@ -200,6 +200,41 @@ def test_generate_dataset_is_reproducible_and_gpu_count_invariant(programs, tmp_
     assert not np.array_equal(outs[0][0], outs[0][1])              # different batches differ
 
 
+def test_ztest_and_compute_cp_gpu_count_invariant(programs, tmp_path, torch_cuda, workloads):
+    """ztest / compute_collision_probability --gpus 2 write the same files as --gpus 1 (needs >= 2 GPUs)."""
+    if torch_cuda.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    data = tmp_path / "data"
+    r = subprocess.run([programs["generate_dataset"], "--data_dir", str(data), "-n", "1", "-b", "2001", "--num_poses", "100",
+                        "--num_variances", "100", "--max_samples", "30000", "--seed", "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    b0 = np.load(data / "0.npy")
+    (data / "tmp").mkdir()
+    np.save(data / "tmp" / "0.npy", np.ascontiguousarray(b0[:, [0, 1, 3, 4]]))
+    outs = []
+    for g in ("1", "2"):
+        out = tmp_path / f"zt{g}.npy"
+        r = subprocess.run([programs["ztest"], "--data_dir", str(data), "--data_file_out", str(out), "--max_samples", "30000", "--seed", "9",
+                            "--meta_dir", str(data / "meta"), "--gpus", g], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr + r.stdout
+        outs.append(np.load(out))
+    np.testing.assert_array_equal(outs[0], outs[1])
+    din = tmp_path / "din"; din.mkdir()
+    np.save(din / "0.npy", np.ascontiguousarray(b0[:777, [0, 1, 3, 4]]))
+    res = []
+    for g in ("1", "2"):
+        dout = tmp_path / f"dout{g}"; (dout / "meta").mkdir(parents=True)
+        for f in ("poses.npy", "variances.npy"):
+            np.save(dout / f, np.load(data / f))
+        for f in ("accuracy_bins.npy", "bin_accuracy.npy"):
+            np.save(dout / "meta" / f, np.load(data / "meta" / f))
+        r = subprocess.run([programs["compute_collision_probability"], "--data_in", str(din), "--data_out", str(dout), "--max_samples",
+                            "30000", "--seed", "4", "--gpus", g], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr + r.stdout
+        res.append(np.load(dout / "0.npy"))
+    np.testing.assert_array_equal(res[0], res[1])
+
+
 def test_program_errors(programs, tmp_path):
     r = subprocess.run([programs["ztest"], "--data_dir", str(tmp_path / "missing")], capture_output=True, text=True)
     assert r.returncode == 1 and "does not exist" in r.stdout
