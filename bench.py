@@ -371,6 +371,13 @@ def extras(ctx, mod, wl, torch, hbm_peak, src):
     sweep = wl.variance_sweep_pairs(1000, 5); d_sw = put(sweep); d_hs = torch.zeros(sweep.size, dtype=torch.int64, device="cuda")
     ms = timed(lambda: ctx.count_fused(d_sw, sweep.size, 100_000, 7, d_hs), reps=3)
     out["cfg5_fused"] = {"tests_per_s": sweep.size * 1e5 / ms * 1e3, "ms": ms, "rows": int(sweep.size), "samples": 100_000}
+    grid = np.array([0.01, 0.05, 0.15, 0.3]); vx, vy, vt = np.meshgrid(grid, grid, grid, indexing="ij")
+    sig = np.sqrt(np.stack([vx.ravel(), vy.ravel(), vt.ravel()], 1)).astype(np.float32)
+    base = wl.dataset_pairs(1000, 5); d_base = put(base); d_sig = torch.from_numpy(sig.ravel()).cuda()
+    ms = timed(lambda: ctx.count_fused_sweep(d_base, base.size, d_sig, 64, 100_000, 7, d_hs), reps=3)
+    out["cfg5_fused_sweep_common_random_numbers"] = {"tests_per_s": base.size * 64 * 1e5 / ms * 1e3, "ms": ms, "rows": int(base.size * 64),
+                                                     "samples": 100_000, "what": "satmc_count_fused_sweep: 64 covariance settings per pair "
+                                                     "share one Philox stream (the sampler runs once per sample, not once per setting)"}
     zb = torch.randn(3 * 100_000, device="cuda")
     ms = timed(lambda: ctx.count_streamed(d_sw, sweep.size, zb, 100_000, 3, 100_000, d_hs), reps=3)
     out["cfg5_streamed_shared_bank"] = {"tests_per_s": sweep.size * 1e5 / ms * 1e3, "ms": ms}

@@ -43,7 +43,7 @@ POLY_PAIR_DTYPE = np.dtype([("rx", "<f4"), ("ry", "<f4"), ("rtheta", "<f4"), ("s
 ABI_SYMBOLS = (
     "satmc_create", "satmc_destroy", "satmc_synchronize", "satmc_last_error", "satmc_version",
     "satmc_launch_count", "satmc_set_profiling", "satmc_last_kernel_ms",
-    "satmc_count_fused", "satmc_count_streamed", "satmc_decide_streamed", "satmc_fused_normals",
+    "satmc_count_fused", "satmc_count_fused_sweep", "satmc_count_streamed", "satmc_decide_streamed", "satmc_fused_normals",
     "satmc_philox_blocks", "satmc_sat_corners", "satmc_exact_evals", "satmc_screen_debug",
     "satmc_count_fused_polygons", "satmc_count_streamed_polygons",
     "satmc_mc_step", "satmc_write_collision_probability", "satmc_adaptive_run", "satmc_sample_positions",
@@ -83,6 +83,7 @@ def load_library() -> ctypes.CDLL:
         "satmc_set_profiling": (i32, [vp, i32]),
         "satmc_last_kernel_ms": (c.c_float, [vp]),
         "satmc_count_fused": (i32, [vp, vp, u64, u64, u64, u64, u32, vp, u32]),
+        "satmc_count_fused_sweep": (i32, [vp, vp, u64, f32p, u32, u64, u64, u64, u32, vp, u32]),
         "satmc_count_streamed": (i32, [vp, vp, u64, f32p, u64, u64, i32, u64, vp, u32]),
         "satmc_decide_streamed": (i32, [vp, vp, f32p, u64, i32, u64, vp, u32]),
         "satmc_fused_normals": (i32, [vp, u64, u32, u64, u64, i32, f32p, u64]),
@@ -215,6 +216,10 @@ class Context:
     def count_fused(self, d_pairs, n_pairs, n_samples, seed, d_hits, sample_offset=0, pair_id_offset=0, flags=0):
         self._check(self._lib.satmc_count_fused(self._h, _ptr(d_pairs), n_pairs, n_samples, seed, sample_offset,
                                                 pair_id_offset, _ptr(d_hits), flags))
+
+    def count_fused_sweep(self, d_pairs, n_pairs, d_sigmas, n_cov, n_samples, seed, d_hits, sample_offset=0, pair_id_offset=0, flags=0):
+        self._check(self._lib.satmc_count_fused_sweep(self._h, _ptr(d_pairs), n_pairs, _ptr(d_sigmas), n_cov, n_samples, seed,
+                                                      sample_offset, pair_id_offset, _ptr(d_hits), flags))
 
     def count_streamed(self, d_pairs, n_pairs, d_z, ldz, ndof, n_samples, d_hits, z_pair_stride=0, flags=0):
         self._check(self._lib.satmc_count_streamed(self._h, _ptr(d_pairs), n_pairs, _ptr(d_z), ldz, z_pair_stride,

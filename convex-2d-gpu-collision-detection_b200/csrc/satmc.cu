@@ -457,6 +457,44 @@ int satmc_count_streamed_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs
     return SATMC_OK;
 }
 
+int satmc_count_fused_sweep(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pairs, const float* d_sigmas, uint32_t n_cov,
+                            uint64_t n_samples, uint64_t seed, uint64_t sample_offset, uint32_t pair_id_offset, uint64_t* d_hits,
+                            uint32_t flags)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    if ((!d_pairs || !d_hits || !d_sigmas) && n_pairs && n_cov) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
+    if (n_pairs > 0xffffffffull - pair_id_offset) return fail(ctx, SATMC_ERR_INVALID, "pair ids exceed 32 bits");
+    if (((uintptr_t)d_pairs & 15u) != 0) return fail(ctx, SATMC_ERR_INVALID, "d_pairs must be 16-byte aligned");
+    if (n_pairs == 0 || n_cov == 0) return SATMC_OK;
+    DeviceGuard g(ctx->device);
+    if (n_samples == 0) {
+        if (!(flags & SATMC_ACCUMULATE)) CU(ctx, cudaMemsetAsync(d_hits, 0, n_pairs * n_cov * sizeof(uint64_t), ctx->stream));
+        return SATMC_OK;
+    }
+    CountParams p{};
+    p.n_pairs = n_pairs; p.n_samples = n_samples; p.sample_offset = sample_offset; p.pair_id_offset = pair_id_offset;
+    philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), p.keys);
+    p.flags = flags | SATMC_ACCUMULATE;                 // plan_items must not clear n_pairs counters: the output is n_pairs x n_cov
+    p.hits = reinterpret_cast<unsigned long long*>(d_hits); p.exact_evals = ctx->d_exact_evals;
+    uint64_t blocks = 0;
+    int rc = plan_items(ctx, p, 2, blocks);
+    if (rc) return rc;
+    p.flags = flags;
+    if (p.n_chunks > 1) p.flags |= SATMC_ACCUMULATE;
+    if (p.n_chunks > 1 && !(flags & SATMC_ACCUMULATE))
+        CU(ctx, cudaMemsetAsync(d_hits, 0, n_pairs * n_cov * sizeof(uint64_t), ctx->stream));
+    // settings are processed kSweepMax at a time; every slice sees the same normals
+    for (uint32_t c0 = 0; c0 < n_cov; c0 += kSweepMax) {
+        const int nc = (int)((n_cov - c0 < (uint32_t)kSweepMax) ? n_cov - c0 : kSweepMax);
+        if (nc != (int)n_cov || c0 != 0)
+            return fail(ctx, SATMC_ERR_INVALID, "n_cov must be <= %d (got %u)", kSweepMax, n_cov);
+        k_count_sweep<<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(d_pairs, d_sigmas, nc, p);
+        CU(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    return SATMC_OK;
+}
+
 static int mc_step_impl(satmc_ctx* ctx, const float* d_robot_base, const float* d_poses, uint32_t n_poses,
                         const float* d_std_devs, uint32_t n_std, const float* d_pose_idxs, const float* d_std_dev_idxs,
                         const float* d_positions, float* d_cps, const float* d_accuracy_bins, const float* d_bin_accuracy,

@@ -460,6 +460,148 @@ k_count_streamed_tma(const __grid_constant__ DirectSrc src, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
+// covariance sweep with common random numbers (BASELINE cfg 5, the ztest-style variance sweep)
+//
+// Every pair is evaluated under n_cov pose-covariance settings (sd_x, sd_y, sd_theta) on the SAME normals: setting c
+// of pair p sees exactly the samples satmc_count_fused would give a pair with that sigma and stream id p.  The
+// sampler (47 % of the issue slots of the plain fused loop) is then paid once per sample instead of once per
+// (sample, setting): a lane draws two 4-sample groups (24 normals) and runs the 22-instruction screening test for all
+// settings from shared-memory constants.  Counts per setting are warp-reduced into shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSweepMax = 64;
+
+struct SweepShared {
+    float4 k[kSweepMax];          // nkx0, nky0, kx1, nky1
+    float2 e[kSweepMax];          // nst, eps
+    float sig[kSweepMax][3];      // sd_x, sd_y, sd_theta (cold path)
+    unsigned cnt[kSweepMax];
+    float robot[8];
+    PairConst base;               // setting-independent constants, for the out-of-line paths
+};
+
+// one sample of one setting, screening + exact fallback (edges and undecided samples)
+__device__ __noinline__ unsigned sweep_sample_slow(const SweepShared& S, int c, float z0, float z1, float z2,
+                                                   unsigned long long* exact_evals)
+{
+    PairConst Q = S.base;
+    const float4 k = S.k[c]; const float2 e = S.e[c];
+    Q.nkx0 = k.x; Q.nky0 = k.y; Q.kx1 = k.z; Q.nky1 = k.w; Q.nst = e.x; Q.eps = e.y;
+    float hmin;
+    const float m = screen_gap<3>(Q, z0, z1, z2, 0.f, 0.f, hmin);
+    unsigned hit = __float_as_uint(m) >> 31;
+    if (!screen_decided<3>(Q, m, hmin)) {
+        hit = (unsigned)exact_decide(S.robot, Q.ow, Q.oh, S.sig[c][0], S.sig[c][1], S.sig[c][2], 0.f, 0.f, z0, z1, z2, 0.f, 0.f);
+        if (exact_evals) atomicAdd(exact_evals, 1ull);
+    }
+    return hit;
+}
+
+// all 8 samples of super-group q (groups 2q, 2q+1) for setting c, normals regenerated: rare path of the main loop
+__device__ __noinline__ unsigned sweep_octet_slow(const SweepShared& S, int c, uint64_t q, uint32_t pid,
+                                                  const PhiloxKeys& K, unsigned long long* exact_evals)
+{
+    unsigned cnt = 0;
+    for (int h = 0; h < 2; h++) {
+        float n[12];
+        const uint64_t g = 2 * q + h;
+        group_normals<3>((uint32_t)g, (uint32_t)(g >> 32), pid, K, n);
+        for (int t = 0; t < 4; t++) cnt += sweep_sample_slow(S, c, n[3 * t], n[3 * t + 1], n[3 * t + 2], exact_evals);
+    }
+    return cnt;
+}
+
+__global__ void __launch_bounds__(kThreads, 2) k_count_sweep(const satmc_pair* __restrict__ pairs, const float* __restrict__ sigmas,
+                                                             int n_cov, const __grid_constant__ CountParams p)
+{
+    __shared__ SweepShared s_sw[kWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    SweepShared& S = s_sw[warp];
+    const uint64_t stride = (uint64_t)gridDim.x * kWarps;
+    for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < p.n_items; item += stride) {
+        const uint64_t pair = item / p.n_chunks;
+        const uint32_t chunk_id = (uint32_t)(item - pair * p.n_chunks);
+        float v[12];
+        DirectSrc src{pairs};
+        src.load(pair, v);
+        PairConst P;                                                   // setting-independent part (sigma fields overridden below)
+        pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], 0.f, 0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+        for (int c = lane; c < n_cov; c += 32) {                       // per-setting constants, two settings per lane
+            const float sx = __ldg(sigmas + 3 * c), sy = __ldg(sigmas + 3 * c + 1), st = __ldg(sigmas + 3 * c + 2);
+            float ea, eb;
+            screen_eps(v[0], v[1], v[2], P.a0, P.a1, P.b0, P.b1, sx, sy, st, 0.f, 0.f, ea, eb);
+            const float hmin = fminf(P.b0, P.b1);
+            const float e3 = ea + __fdividef(eb, hmin);
+            const bool ok = hmin > 0.0f && e3 == e3 && !(p.flags & SATMC_EXACT_ONLY);
+            S.k[c] = make_float4(-(sx * P.ca), -(sy * P.sa), sx * P.sa, -(sy * P.ca));
+            S.e[c] = make_float2(-st, ok ? e3 : CUDART_INF_F);
+            S.sig[c][0] = sx; S.sig[c][1] = sy; S.sig[c][2] = st;
+            S.cnt[c] = 0;
+        }
+        if (lane == 0) { exact_robot_corners(v[0], v[1], P.ca, P.sa, v[3], v[4], S.robot); S.base = P; }
+        __syncwarp();
+        const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
+        const uint64_t c_len = (c_begin + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - c_begin);
+        unsigned long long* ev = (p.flags & SATMC_EXACT_ONLY) ? nullptr : p.exact_evals;
+        const uint32_t pid = p.pair_id_offset + (uint32_t)pair;
+        const uint64_t b = p.sample_offset + c_begin, e = b + c_len;
+        const uint64_t q_lo = (b + 7) >> 3, q_hi = e >> 3;              // full 8-sample super-groups [q_lo, q_hi)
+        if (q_lo <= q_hi) {
+            for (uint64_t q0 = q_lo; q0 < q_hi; q0 += 32) {             // all 32 lanes stay in step; idle lanes count nothing
+                const uint64_t q = q0 + (uint64_t)lane;
+                const bool mine = q < q_hi;
+                float n[24];
+                group_normals<3>((uint32_t)(2 * q), (uint32_t)((2 * q) >> 32), pid, p.keys, n);
+                group_normals<3>((uint32_t)(2 * q + 1), (uint32_t)((2 * q + 1) >> 32), pid, p.keys, n + 12);
+                for (int c = 0; c < n_cov; c++) {
+                    const float4 k = S.k[c]; const float2 ee = S.e[c];
+                    PairConst Q = P;
+                    Q.nkx0 = k.x; Q.nky0 = k.y; Q.kx1 = k.z; Q.nky1 = k.w; Q.nst = ee.x; Q.eps = ee.y;
+                    unsigned cnt = 0;
+                    bool decided = true;
+#pragma unroll
+                    for (int t = 0; t < 8; t++) {
+                        float hmin;
+                        const float m = screen_gap<3>(Q, n[3 * t], n[3 * t + 1], n[3 * t + 2], 0.f, 0.f, hmin);
+                        cnt += __float_as_uint(m) >> 31;
+                        decided = decided && screen_decided<3>(Q, m, hmin);
+                    }
+                    if (!decided && mine) cnt = sweep_octet_slow(S, c, q, pid, p.keys, ev);
+                    cnt = __reduce_add_sync(0xffffffffu, mine ? cnt : 0u);
+                    if (lane == 0) S.cnt[c] += cnt;
+                }
+            }
+        }
+        __syncwarp();
+        // ragged ends: samples of [b, e) outside the full super-groups; lanes parallelise over settings
+        const uint64_t head_end = (q_lo <= q_hi) ? ((q_lo << 3) < e ? (q_lo << 3) : e) : e;
+        const uint64_t tail_begin = (q_lo <= q_hi) ? (q_hi << 3) : e;
+        for (int part = 0; part < 2; part++) {
+            const uint64_t lo = part ? (tail_begin > head_end ? tail_begin : head_end) : b;
+            const uint64_t hi = part ? e : head_end;
+            for (uint64_t sidx = lo; sidx < hi; sidx++) {
+                float n[12];
+                group_normals<3>((uint32_t)(sidx >> 2), (uint32_t)((sidx >> 2) >> 32), pid, p.keys, n);
+                const int t = (int)(sidx & 3);
+                float z0 = n[0], z1 = n[1], z2 = n[2];
+                if (t == 1) { z0 = n[3]; z1 = n[4]; z2 = n[5]; }
+                if (t == 2) { z0 = n[6]; z1 = n[7]; z2 = n[8]; }
+                if (t == 3) { z0 = n[9]; z1 = n[10]; z2 = n[11]; }
+                for (int c = lane; c < n_cov; c += 32) S.cnt[c] += sweep_sample_slow(S, c, z0, z1, z2, ev);
+            }
+        }
+        __syncwarp();
+        for (int c = lane; c < n_cov; c += 32) {
+            const unsigned long long tot = S.cnt[c];
+            unsigned long long* dst = p.hits + pair * (uint64_t)n_cov + c;
+            if (p.n_chunks == 1) { if (p.flags & SATMC_ACCUMULATE) *dst += tot; else *dst = tot; }
+            else atomicAdd(dst, tot);
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // general convex polygons: same work decomposition, sampler and counting as k_count;
 // every sample is evaluated with the exact polygon SAT of satmc_poly.cuh (no screening pass yet)
 // ---------------------------------------------------------------------------------------------

@@ -101,6 +101,15 @@ int satmc_count_fused(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pair
                       uint64_t n_samples, uint64_t seed, uint64_t sample_offset,
                       uint32_t pair_id_offset, uint64_t* d_hits, uint32_t flags);
 
+/* Covariance sweep with common random numbers (the ztest-style variance sweep, BASELINE config 5): every pair is
+ * evaluated under n_cov <= 64 pose-covariance settings d_sigmas[c] = (sd_x, sd_y, sd_theta) on the same normals.
+ * d_hits[i*n_cov + c] equals what satmc_count_fused returns for pair i with sd_* = d_sigmas[c], sd_w = sd_h = 0 and
+ * the same (seed, pair id, sample range) -- bit for bit -- but the sampler runs once per sample instead of once
+ * per (sample, setting).  The sd_* fields of d_pairs are ignored. */
+int satmc_count_fused_sweep(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pairs, const float* d_sigmas,
+                            uint32_t n_cov, uint64_t n_samples, uint64_t seed, uint64_t sample_offset,
+                            uint32_t pair_id_offset, uint64_t* d_hits, uint32_t flags);
+
 /* Streamed path: the normals are supplied by the caller (verification against the reference on
  * shared samples; HBM-bound).  d_z is SoA: plane k (k = 0..ndof-1 = x, y, theta[, w, h]) of sample
  * s is d_z[k*ldz + s].  Pair i consumes samples [i*z_pair_stride, i*z_pair_stride + n_samples) of

@@ -413,6 +413,52 @@ def test_fused_vs_reference_kernel_statistically(ctx, dev, refgpu, workloads):
     assert 0.02 < (cps > 0).mean()                                  # the workload has real hits
 
 
+# ---- covariance sweep with common random numbers -------------------------------------------------------------------
+@pytest.mark.parametrize("n,offset", [(4096, 0), (1000, 0), (4099, 3), (7, 5), (20_001, 123_456_789_013)])
+def test_sweep_equals_fused_per_setting(ctx, dev, workloads, n, offset):
+    """satmc_count_fused_sweep[i, c] == satmc_count_fused(pair i with sigma c, same stream id), bit for bit."""
+    pairs = workloads.dataset_pairs(23, seed=97)
+    rng = np.random.default_rng(n)
+    n_cov = 37 if n != 4096 else 64
+    sig = np.sqrt(rng.uniform(0.0, 0.3, (n_cov, 3))).astype(np.float32)
+    sig[0] = 0.0                                                     # a setting with no uncertainty at all
+    d_pairs = dev.put(pairs); d_sig = dev.put(sig.ravel())
+    for flags in (0, EXACT):
+        d_hits = dev.zeros(pairs.size * n_cov, np.uint64)
+        ctx.count_fused_sweep(d_pairs, pairs.size, d_sig, n_cov, n, 321, d_hits, sample_offset=offset, pair_id_offset=11, flags=flags)
+        ctx.synchronize()
+        got = dev.get(d_hits, np.uint64).reshape(pairs.size, n_cov)
+        for c in range(0, n_cov, 5 if flags else 1):
+            q = pairs.copy(); q["sd_x"] = sig[c, 0]; q["sd_y"] = sig[c, 1]; q["sd_theta"] = sig[c, 2]; q["sd_w"] = 0; q["sd_h"] = 0
+            want = fused(ctx, dev, q, n, 321, sample_offset=offset, pair_id_offset=11)
+            np.testing.assert_array_equal(got[:, c], want, err_msg=f"setting {c} flags {flags}")
+    # accumulate + single pair split into many chunks
+    d_hits = dev.zeros(n_cov, np.uint64)
+    ctx.count_fused_sweep(dev.put(pairs[:1]), 1, d_sig, n_cov, n, 321, d_hits, sample_offset=offset, pair_id_offset=11)
+    ctx.count_fused_sweep(dev.put(pairs[:1]), 1, d_sig, n_cov, n, 321, d_hits, sample_offset=offset, pair_id_offset=11, flags=ACC)
+    ctx.synchronize()
+    np.testing.assert_array_equal(dev.get(d_hits, np.uint64), 2 * got[0])
+
+
+def test_sweep_cfg5_full_size(ctx, dev, workloads):
+    """cfg 5 at full size through the sweep entry point (1e4 pairs x 64 settings x 1e5 samples): agrees with the plain fused
+    path row by row within the binomial bound (different streams: the sweep shares one stream per pair)."""
+    base = workloads.dataset_pairs(10_000, seed=5)
+    grid = np.array([0.01, 0.05, 0.15, 0.3])
+    vx, vy, vt = np.meshgrid(grid, grid, grid, indexing="ij")
+    sig = np.sqrt(np.stack([vx.ravel(), vy.ravel(), vt.ravel()], 1)).astype(np.float32)
+    n = 100_000
+    d_hits = dev.zeros(base.size * 64, np.uint64)
+    ctx.count_fused_sweep(dev.put(base), base.size, dev.put(sig.ravel()), 64, n, 77, d_hits)
+    ctx.synchronize()
+    k_sweep = dev.get(d_hits, np.uint64).astype(np.float64)
+    rows = workloads.variance_sweep_pairs(10_000, seed=5)
+    k_f = fused(ctx, dev, rows, n, 2025).astype(np.float64)
+    p = (k_sweep + k_f) / (2 * n)
+    viol = np.abs(k_sweep - k_f) > 4.9 * np.sqrt(2 * n * p * (1 - p)) + 1
+    assert viol.sum() <= 2, int(viol.sum())
+
+
 # ---- BASELINE.json full sizes through size-independent properties ------------------------------------------
 def test_cfg4_full_size_sharding_property(ctx, dev, workloads):
     """Single pair, N = 1e10: the count is the sum of the counts of 4 unequal sample ranges (what the NCCL all-reduce

@@ -8,7 +8,14 @@ wl = importlib.import_module("convex-2d-gpu-collision-detection_b200.workloads")
 mode = sys.argv[1] if len(sys.argv) > 1 else "fused"
 ctx = satmc.Context(0, torch.cuda.current_stream().cuda_stream)
 put = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.float32)).cuda()
-if mode in ("fused", "fused5", "ztest"):
+if mode == "sweep":
+    base = wl.dataset_pairs(10_000, 5)
+    grid = np.array([0.01, 0.05, 0.15, 0.3]); vx, vy, vt = np.meshgrid(grid, grid, grid, indexing="ij")
+    sig = np.sqrt(np.stack([vx.ravel(), vy.ravel(), vt.ravel()], 1)).astype(np.float32)
+    d_pairs = put(base); d_s = torch.from_numpy(sig.ravel()).cuda(); d_hits = torch.zeros(base.size * 64, dtype=torch.int64, device="cuda")
+    for _ in range(3):
+        ctx.count_fused_sweep(d_pairs, base.size, d_s, 64, 20_000, 7, d_hits)
+elif mode in ("fused", "fused5", "ztest"):
     pairs = wl.dataset_pairs(100_000, 3, shape_variance=(mode == "fused5"))
     n = 1000 if mode == "ztest" else 10_000
     d_pairs = put(pairs); d_hits = torch.zeros(pairs.size, dtype=torch.int64, device="cuda")
