@@ -335,6 +335,14 @@ def test_fused_normals_distribution_and_oracle_agreement(ctx, dev, oracle):
         assert abs((np.abs(z[k]) > 3).sum() - n * p) < 4.9 * math.sqrt(n * p)
     zo = np.stack([oracle.fused_normals(99, 3, (1 << 33) + 1 + i, 5) for i in range(2000)], 1)
     assert np.abs(z[:, :2000] - zo).max() < 4e-6                               # same formula, MUFU vs libm
+    # consecutive samples share Philox blocks and Box-Muller pairs (theta of sample 4g and x of sample 4g+1 are the cos
+    # and sin outputs of one pair): they must still be independent, also in their squares (shared radius)
+    z3big = fused_normals(ctx, dev, 7, 1, 0, n, 3).astype(np.float64)
+    a, b = z3big[2, 0::4], z3big[0, 1::4]
+    m = a.size
+    assert abs(np.corrcoef(a, b)[0, 1]) < 4.9 / math.sqrt(m)
+    assert abs(np.corrcoef(a ** 2, b ** 2)[0, 1]) < 4.9 / math.sqrt(m)
+    assert abs(np.corrcoef(z3big[0, :-1], z3big[0, 1:])[0, 1]) < 4.9 / math.sqrt(n)
     z3 = fused_normals(ctx, dev, 99, 3, 5, 4001, 3)                            # 3-DoF pairs use the stream differently
     zo3 = np.stack([oracle.fused_normals(99, 3, 5 + i, 3) for i in range(4001)], 1)
     assert np.abs(z3 - zo3).max() < 4e-6
