@@ -486,9 +486,9 @@ int satmc_count_fused_sweep(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t 
     // settings are processed kSweepMax at a time; every slice sees the same normals
     for (uint32_t c0 = 0; c0 < n_cov; c0 += kSweepMax) {
         const int nc = (int)((n_cov - c0 < (uint32_t)kSweepMax) ? n_cov - c0 : kSweepMax);
-        if (nc != (int)n_cov || c0 != 0)
-            return fail(ctx, SATMC_ERR_INVALID, "n_cov must be <= %d (got %u)", kSweepMax, n_cov);
-        k_count_sweep<<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(d_pairs, d_sigmas, nc, p);
+        CountParams q = p;
+        q.hits = p.hits + c0;
+        k_count_sweep<<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(d_pairs, d_sigmas + 3 * (size_t)c0, nc, (uint64_t)n_cov, q);
         CU(ctx, cudaGetLastError());
         ctx->launches++;
     }

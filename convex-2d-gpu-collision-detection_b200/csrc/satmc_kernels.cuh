@@ -511,7 +511,7 @@ __device__ __noinline__ unsigned sweep_octet_slow(const SweepShared& S, int c, u
 }
 
 __global__ void __launch_bounds__(kThreads, 2) k_count_sweep(const satmc_pair* __restrict__ pairs, const float* __restrict__ sigmas,
-                                                             int n_cov, const __grid_constant__ CountParams p)
+                                                             int n_cov, uint64_t hits_stride, const __grid_constant__ CountParams p)
 {
     __shared__ SweepShared s_sw[kWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_count_sweep(const satmc_pair* _
         __syncwarp();
         for (int c = lane; c < n_cov; c += 32) {
             const unsigned long long tot = S.cnt[c];
-            unsigned long long* dst = p.hits + pair * (uint64_t)n_cov + c;
+            unsigned long long* dst = p.hits + pair * hits_stride + c;
             if (p.n_chunks == 1) { if (p.flags & SATMC_ACCUMULATE) *dst += tot; else *dst = tot; }
             else atomicAdd(dst, tot);
         }

@@ -102,7 +102,8 @@ int satmc_count_fused(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pair
                       uint32_t pair_id_offset, uint64_t* d_hits, uint32_t flags);
 
 /* Covariance sweep with common random numbers (the ztest-style variance sweep, BASELINE config 5): every pair is
- * evaluated under n_cov <= 64 pose-covariance settings d_sigmas[c] = (sd_x, sd_y, sd_theta) on the same normals.
+ * evaluated under n_cov pose-covariance settings d_sigmas[c] = (sd_x, sd_y, sd_theta) on the same normals (64 settings
+ * per kernel launch).
  * d_hits[i*n_cov + c] equals what satmc_count_fused returns for pair i with sd_* = d_sigmas[c], sd_w = sd_h = 0 and
  * the same (seed, pair id, sample range) -- bit for bit -- but the sampler runs once per sample instead of once
  * per (sample, setting).  The sd_* fields of d_pairs are ignored. */

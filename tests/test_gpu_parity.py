@@ -427,7 +427,7 @@ def test_sweep_equals_fused_per_setting(ctx, dev, workloads, n, offset):
     """satmc_count_fused_sweep[i, c] == satmc_count_fused(pair i with sigma c, same stream id), bit for bit."""
     pairs = workloads.dataset_pairs(23, seed=97)
     rng = np.random.default_rng(n)
-    n_cov = 37 if n != 4096 else 64
+    n_cov = {4096: 64, 1000: 100}.get(n, 37)                         # 100 settings = two kernel launches
     sig = np.sqrt(rng.uniform(0.0, 0.3, (n_cov, 3))).astype(np.float32)
     sig[0] = 0.0                                                     # a setting with no uncertainty at all
     d_pairs = dev.put(pairs); d_sig = dev.put(sig.ravel())
