@@ -619,13 +619,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_count_poly(const float* __restr
         if (lane == 0) poly_prologue(s_poly[warp], pairs + pair * 40);          // 160-byte descriptors
         __syncwarp();
         const PolyPairShared& S = s_poly[warp];
+        PolyRobotRegs R;
+        poly_load_robot(S, R);
         const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
         const uint64_t c_len = (c_begin + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - c_begin);
         unsigned cnt = 0;
         if (STREAMED) {
             const float* z = p.z + pair * p.z_pair_stride + c_begin;
             for (uint64_t i = (uint64_t)lane; i < c_len; i += 32)
-                cnt += poly_collide(S, __ldg(z + i), __ldg(z + p.ldz + i), __ldg(z + 2 * p.ldz + i));
+                cnt += poly_collide(S, R, __ldg(z + i), __ldg(z + p.ldz + i), __ldg(z + 2 * p.ldz + i));
         } else {
             const uint32_t pid = p.pair_id_offset + (uint32_t)pair;
             const uint64_t b = p.sample_offset + c_begin, e = b + c_len;
@@ -635,7 +637,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_count_poly(const float* __restr
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
                     const uint64_t sidx = 4 * g + t;
-                    if (sidx >= b && sidx < e) cnt += poly_collide(S, n[3 * t], n[3 * t + 1], n[3 * t + 2]);
+                    if (sidx >= b && sidx < e) cnt += poly_collide(S, R, n[3 * t], n[3 * t + 1], n[3 * t + 2]);
                 }
             }
         }

@@ -7,7 +7,7 @@
 //   robot vertex    x' = FADD(FFMA(x, c, -FMUL(y, s)), px)          (rot_trans_rectangle as compiled, utils.cu:132-142)
 //   obstacle vertex x' = FFMA(z0, sd_x, FFMA(x, c, -FMUL(y, s)))    (sample_rectangle as compiled, utils.cu:144-157)
 //   projection      p(q) = FFMA(n.x, q.x, FMUL(n.y, q.y))           (utils.cu:173-174)
-//   min/max seeded by the first vertex, strict <; separated iff max1 < min2 || max2 < min1; ties and NaN collide
+//   min/max = fminf/fmaxf over the vertices; separated iff max1 < min2 || max2 < min1 (strict); ties collide
 // Every rounding is pinned with intrinsics, so a CPU restatement of the same sequence (the test suite has one)
 // gives bit-identical decisions.  Vertices are counter-clockwise, 1..8 per polygon.
 #pragma once
@@ -51,14 +51,24 @@ __device__ __forceinline__ void poly_prologue(PolyPairShared& S, const float* __
         float mn = 0.f, mx = 0.f;
         for (int k = 0; k < nr; k++) {
             const float p = __fmaf_rn(nx, S.rob_x[k], __fmul_rn(ny, S.rob_y[k]));
-            if (k == 0) { mn = mx = p; } else { if (p < mn) mn = p; if (mx < p) mx = p; }
+            if (k == 0) { mn = mx = p; } else { mn = fminf(mn, p); mx = fmaxf(mx, p); }
         }
         S.rnx[i] = nx; S.rny[i] = ny; S.rmin[i] = mn; S.rmax[i] = mx;
     }
 }
 
-// decision for one sample: 1 = overlap
-__device__ __forceinline__ unsigned poly_collide(const PolyPairShared& S, float z0, float z1, float z2)
+// robot vertices of the current pair in registers (loaded once per work item)
+struct PolyRobotRegs { float x[kPolyMax], y[kPolyMax]; };
+
+__device__ __forceinline__ void poly_load_robot(const PolyPairShared& S, PolyRobotRegs& R)
+{
+#pragma unroll
+    for (int k = 0; k < kPolyMax; k++) { R.x[k] = (k < S.nr) ? S.rob_x[k] : 0.f; R.y[k] = (k < S.nr) ? S.rob_y[k] : 0.f; }
+}
+
+// decision for one sample: 1 = overlap.  nr, no are warp-uniform, so the `break`s below are uniform branches and a
+// quad-quad pair does half the work of an octagon-octagon pair.
+__device__ __forceinline__ unsigned poly_collide(const PolyPairShared& S, const PolyRobotRegs& R, float z0, float z1, float z2)
 {
     const int nr = S.nr, no = S.no;
     const float dt = __fmul_rn(z2, S.sd_t);
@@ -66,50 +76,49 @@ __device__ __forceinline__ unsigned poly_collide(const PolyPairShared& S, float 
     float ox[kPolyMax], oy[kPolyMax];
 #pragma unroll
     for (int k = 0; k < kPolyMax; k++) {
-        if (k < no) {
-            const float x = S.obs_x[k], y = S.obs_y[k];
-            ox[k] = __fmaf_rn(z0, S.sd_x, __fmaf_rn(x, c, -__fmul_rn(y, s)));
-            oy[k] = __fmaf_rn(z1, S.sd_y, __fmaf_rn(x, s, __fmul_rn(y, c)));
-        } else { ox[k] = 0.f; oy[k] = 0.f; }
+        if (k >= no) break;
+        const float x = S.obs_x[k], y = S.obs_y[k];
+        ox[k] = __fmaf_rn(z0, S.sd_x, __fmaf_rn(x, c, -__fmul_rn(y, s)));
+        oy[k] = __fmaf_rn(z1, S.sd_y, __fmaf_rn(x, s, __fmul_rn(y, c)));
     }
     bool sep = false;
     // robot normals: the robot's own extent is a per-pair constant
-    for (int i = 0; i < nr; i++) {
-        const float nx = S.rnx[i], ny = S.rny[i];
-        float mn = 0.f, mx = 0.f;
 #pragma unroll
-        for (int k = 0; k < kPolyMax; k++) {
-            if (k < no) {
-                const float p = __fmaf_rn(nx, ox[k], __fmul_rn(ny, oy[k]));
-                if (k == 0) { mn = mx = p; } else { if (p < mn) mn = p; if (mx < p) mx = p; }
-            }
+    for (int i = 0; i < kPolyMax; i++) {
+        if (i >= nr) break;
+        const float nx = S.rnx[i], ny = S.rny[i];
+        float mn = __fmaf_rn(nx, ox[0], __fmul_rn(ny, oy[0])), mx = mn;
+#pragma unroll
+        for (int k = 1; k < kPolyMax; k++) {
+            if (k >= no) break;
+            const float p = __fmaf_rn(nx, ox[k], __fmul_rn(ny, oy[k]));
+            mn = fminf(mn, p); mx = fmaxf(mx, p);
         }
         sep = sep || (S.rmax[i] < mn) || (mx < S.rmin[i]);
     }
     // obstacle normals
 #pragma unroll
     for (int i = 0; i < kPolyMax; i++) {
-        if (i < no) {
-            const int j = (i + 1 == no) ? 0 : i + 1;
-            float jx = ox[0], jy = oy[0];
+        if (i >= no) break;
+        const float jx = (i + 1 < kPolyMax && i + 1 < no) ? ox[(i + 1) % kPolyMax] : ox[0];
+        const float jy = (i + 1 < kPolyMax && i + 1 < no) ? oy[(i + 1) % kPolyMax] : oy[0];
+        const float ex = __fadd_rn(jx, -ox[i]), ey = __fadd_rn(jy, -oy[i]);
+        const float nx = ey, ny = -ex;
+        float mn1 = __fmaf_rn(nx, R.x[0], __fmul_rn(ny, R.y[0])), mx1 = mn1;
 #pragma unroll
-            for (int k = 1; k < kPolyMax; k++) if (k == j) { jx = ox[k]; jy = oy[k]; }
-            const float ex = __fadd_rn(jx, -ox[i]), ey = __fadd_rn(jy, -oy[i]);
-            const float nx = ey, ny = -ex;
-            float mn1 = 0.f, mx1 = 0.f, mn2 = 0.f, mx2 = 0.f;
-            for (int k = 0; k < nr; k++) {
-                const float p = __fmaf_rn(nx, S.rob_x[k], __fmul_rn(ny, S.rob_y[k]));
-                if (k == 0) { mn1 = mx1 = p; } else { if (p < mn1) mn1 = p; if (mx1 < p) mx1 = p; }
-            }
-#pragma unroll
-            for (int k = 0; k < kPolyMax; k++) {
-                if (k < no) {
-                    const float p = __fmaf_rn(nx, ox[k], __fmul_rn(ny, oy[k]));
-                    if (k == 0) { mn2 = mx2 = p; } else { if (p < mn2) mn2 = p; if (mx2 < p) mx2 = p; }
-                }
-            }
-            sep = sep || (mx1 < mn2) || (mx2 < mn1);
+        for (int k = 1; k < kPolyMax; k++) {
+            if (k >= nr) break;
+            const float p = __fmaf_rn(nx, R.x[k], __fmul_rn(ny, R.y[k]));
+            mn1 = fminf(mn1, p); mx1 = fmaxf(mx1, p);
         }
+        float mn2 = __fmaf_rn(nx, ox[0], __fmul_rn(ny, oy[0])), mx2 = mn2;
+#pragma unroll
+        for (int k = 1; k < kPolyMax; k++) {
+            if (k >= no) break;
+            const float p = __fmaf_rn(nx, ox[k], __fmul_rn(ny, oy[k]));
+            mn2 = fminf(mn2, p); mx2 = fmaxf(mx2, p);
+        }
+        sep = sep || (mx1 < mn2) || (mx2 < mn1);
     }
     return sep ? 0u : 1u;
 }
