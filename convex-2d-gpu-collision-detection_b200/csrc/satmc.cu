@@ -248,11 +248,18 @@ static int plan_items(satmc_ctx* ctx, CountParams& p, int bps, uint64_t& blocks)
     p.n_chunks = (uint32_t)n_chunks;
     p.n_items = p.n_pairs * n_chunks;
     p.block_uniform = (n_chunks % kWarps == 0) ? 1u : 0u;
-    if (n_chunks > 1 && !(p.flags & SATMC_ACCUMULATE))
-        CU(ctx, cudaMemsetAsync(p.hits, 0, p.n_pairs * sizeof(unsigned long long), ctx->stream));
     blocks = (p.n_items + kWarps - 1) / kWarps;
     const uint64_t max_blocks = (uint64_t)ctx->sm_count * bps;
     if (blocks > max_blocks) blocks = max_blocks;
+    return SATMC_OK;
+}
+
+// With several chunks per pair the kernels accumulate with atomics: the counters must start from zero unless the
+// caller asked to accumulate.  `counters` = number of 64-bit counters behind p.hits.
+static int clear_hits_for_atomics(satmc_ctx* ctx, const CountParams& p, uint64_t counters, uint32_t user_flags)
+{
+    if (p.n_chunks > 1 && !(user_flags & SATMC_ACCUMULATE))
+        CU(ctx, cudaMemsetAsync(p.hits, 0, counters * sizeof(unsigned long long), ctx->stream));
     return SATMC_OK;
 }
 
@@ -272,6 +279,8 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
     const int bps = tma ? ctx->blocks_per_sm_tma[p.ndof == 5] : (STREAMED ? ctx->blocks_per_sm_streamed : ctx->blocks_per_sm);
     uint64_t blocks = 0;
     int rc = plan_items(ctx, p, bps, blocks);
+    if (rc) return rc;
+    rc = clear_hits_for_atomics(ctx, p, p.n_pairs, p.flags);
     if (rc) return rc;
     if (time_it) CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if constexpr (STREAMED) {
@@ -428,6 +437,8 @@ int satmc_count_fused_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs, u
     uint64_t blocks = 0;
     int rc = plan_items(ctx, p, 2, blocks);
     if (rc) return rc;
+    rc = clear_hits_for_atomics(ctx, p, n_pairs, flags);
+    if (rc) return rc;
     k_count_poly<false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(reinterpret_cast<const float*>(d_pairs), p);
     CU(ctx, cudaGetLastError());
     ctx->launches++;
@@ -450,6 +461,8 @@ int satmc_count_streamed_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs
     }
     uint64_t blocks = 0;
     rc = plan_items(ctx, p, 2, blocks);
+    if (rc) return rc;
+    rc = clear_hits_for_atomics(ctx, p, n_pairs, flags);
     if (rc) return rc;
     k_count_poly<true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(reinterpret_cast<const float*>(d_pairs), p);
     CU(ctx, cudaGetLastError());
@@ -474,15 +487,13 @@ int satmc_count_fused_sweep(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t 
     CountParams p{};
     p.n_pairs = n_pairs; p.n_samples = n_samples; p.sample_offset = sample_offset; p.pair_id_offset = pair_id_offset;
     philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), p.keys);
-    p.flags = flags | SATMC_ACCUMULATE;                 // plan_items must not clear n_pairs counters: the output is n_pairs x n_cov
+    p.flags = flags;
     p.hits = reinterpret_cast<unsigned long long*>(d_hits); p.exact_evals = ctx->d_exact_evals;
     uint64_t blocks = 0;
     int rc = plan_items(ctx, p, 2, blocks);
     if (rc) return rc;
-    p.flags = flags;
-    if (p.n_chunks > 1) p.flags |= SATMC_ACCUMULATE;
-    if (p.n_chunks > 1 && !(flags & SATMC_ACCUMULATE))
-        CU(ctx, cudaMemsetAsync(d_hits, 0, n_pairs * n_cov * sizeof(uint64_t), ctx->stream));
+    rc = clear_hits_for_atomics(ctx, p, n_pairs * n_cov, flags);
+    if (rc) return rc;
     // settings are processed kSweepMax at a time; every slice sees the same normals
     for (uint32_t c0 = 0; c0 < n_cov; c0 += kSweepMax) {
         const int nc = (int)((n_cov - c0 < (uint32_t)kSweepMax) ? n_cov - c0 : kSweepMax);
