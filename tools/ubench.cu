@@ -45,6 +45,19 @@ __global__ void __launch_bounds__(1024, 1) k(uint32_t seed, uint32_t* sink, long
                             f[i] = fmaf(f[i], 1.0000007f, 3e-9f); f[i] = fmaf(f[i], 1.0000008f, 4e-9f); }
             if (OP == 19) { f[i] = fmaf(f[i], 1.0000001f, 1e-9f); f[i] = fmaf(f[i], 1.0000002f, 2e-9f);                      // 4 FFMA (baseline for 17)
                             f[i] = fmaf(f[i], 1.0000003f, 3e-9f); f[i] = fmaf(f[i], 1.0000004f, 4e-9f); }
+            if (OP >= 20 && OP <= 23) {                                                                                     // 16-slot groups: FFMA only / with 1 MUFU / with 2 MUFU / 2 MUFU + 4 FADD|x| + 2 FMNMX
+                float x = f[i];
+                const int nf = OP == 20 ? 16 : OP == 21 ? 15 : OP == 22 ? 14 : 8;
+#pragma unroll
+                for (int r = 0; r < nf; r++) x = fmaf(x, 1.0000001f + r * 1e-7f, 1e-9f);
+                if (OP >= 21) { float g = __uint_as_float(a[i]); float sn, cs = 0.f;
+                                asm volatile("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(g));
+                                if (OP >= 22) asm volatile("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(g));
+                                a[i] = __float_as_uint(sn) ^ __float_as_uint(cs); }
+                if (OP == 23) { float y = fabsf(x) - 0.5f; float z = fabsf(y) - 0.25f; float w = fabsf(z) - 0.125f; float v = fabsf(w) - 0.0625f;
+                                x = fmaxf(fmaxf(y, z), fmaxf(w, v)); }
+                f[i] = x;
+            }
             if (OP == 16) { a[i] = __float_as_uint(f[i] = fmaf(f[i], 1.0000001f, 1e-9f)) >> 31; }                           // FFMA + SHF
         }
     }
@@ -78,5 +91,6 @@ int main()
     run<12>("I2F.U32+LOP3", 2); run<13>("IMAD.HI", 1); run<14>("IMAD.WIDE(+c)", 1); run<15>("MUFU.SQRT", 1);
     run<19>("4 FFMA", 4); run<17>("IMAD.WIDE+LOP3+4 FFMA", 6); run<18>("IMAD.WIDE+LOP3+8 FFMA", 10);
     run<5>("PRMT", 1); run<6>("FMNMX+FMUL", 2); run<4>("MUFU.LG2", 1); run<8>("FMUL+MUFU.SIN", 2); run<9>("FFMA+IMAD", 2); run<10>("FFMA+LOP3x2", 3);
+    run<20>("16 FFMA", 16); run<21>("15 FFMA + MUFU.SIN", 17); run<22>("14 FFMA + SIN + COS", 18); run<23>("8 FFMA+4 FADD+3 FMNMX+SIN+COS", 19);
     return 0;
 }
