@@ -28,6 +28,8 @@ struct satmc_ctx {
     char err[512] = {0};
     uint64_t launches = 0;
     unsigned long long* d_exact_evals = nullptr;
+    unsigned long long* d_ticket = nullptr;  // work-item counter of the dynamically scheduled kernels: never reset,
+    uint64_t ticket_next = 0;                // the host mirrors its value (every processed item draws exactly one ticket)
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
@@ -153,6 +155,8 @@ int satmc_create(int device, void* stream, satmc_ctx** out)
     cudaGetLastError();
     if (cudaMalloc(&ctx->d_exact_evals, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(ctx->d_exact_evals, 0, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_ticket, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(ctx->d_ticket, 0, sizeof(unsigned long long)) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
         int rc = fail(nullptr, SATMC_ERR_CUDA, "context allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete ctx;
@@ -169,6 +173,7 @@ int satmc_destroy(satmc_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 3; i++) if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
     if (ctx->d_exact_evals) cudaFree(ctx->d_exact_evals);
+    if (ctx->d_ticket) cudaFree(ctx->d_ticket);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     delete ctx;
@@ -256,6 +261,16 @@ static int plan_items(satmc_ctx* ctx, CountParams& p, int bps, uint64_t& blocks,
     return SATMC_OK;
 }
 
+// Switches a launch to dynamic work distribution (see CountParams::ticket) when warps get more than one item and need
+// not walk the items in step.  Every processed item draws one ticket, so the counter advances by n_items per launch.
+static void use_tickets(satmc_ctx* ctx, CountParams& p, uint64_t blocks)
+{
+    if (p.block_uniform || p.n_items <= blocks * (uint64_t)kWarps) return;
+    p.ticket = ctx->d_ticket;
+    p.ticket_base = ctx->ticket_next;
+    ctx->ticket_next += p.n_items;
+}
+
 // With several chunks per pair the kernels accumulate with atomics: the counters must start from zero unless the
 // caller asked to accumulate.  `counters` = number of 64-bit counters behind p.hits.
 static int clear_hits_for_atomics(satmc_ctx* ctx, const CountParams& p, uint64_t counters, uint32_t user_flags)
@@ -284,6 +299,8 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
     if (rc) return rc;
     rc = clear_hits_for_atomics(ctx, p, p.n_pairs, p.flags);
     if (rc) return rc;
+    const uint64_t ticket_before = ctx->ticket_next;
+    if (!tma) use_tickets(ctx, p, blocks);
     if (time_it) CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if constexpr (STREAMED) {
         if (tma && p.ndof == 5)
@@ -295,6 +312,7 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
     } else {
         k_count<Src, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
     }
+    if (cudaPeekAtLastError() != cudaSuccess) ctx->ticket_next = ticket_before;       // nothing ran: no ticket was drawn
     CU(ctx, cudaGetLastError());
     if (time_it) { CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream)); ctx->last_ms_valid = true; }
     ctx->launches++;
@@ -441,7 +459,10 @@ int satmc_count_fused_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs, u
     if (rc) return rc;
     rc = clear_hits_for_atomics(ctx, p, n_pairs, flags);
     if (rc) return rc;
+    const uint64_t ticket_before = ctx->ticket_next;
+    use_tickets(ctx, p, blocks);
     k_count_poly<false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(reinterpret_cast<const float*>(d_pairs), p);
+    if (cudaPeekAtLastError() != cudaSuccess) ctx->ticket_next = ticket_before;       // nothing ran: no ticket was drawn
     CU(ctx, cudaGetLastError());
     ctx->launches++;
     return SATMC_OK;
@@ -466,7 +487,10 @@ int satmc_count_streamed_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs
     if (rc) return rc;
     rc = clear_hits_for_atomics(ctx, p, n_pairs, flags);
     if (rc) return rc;
+    const uint64_t ticket_before = ctx->ticket_next;
+    use_tickets(ctx, p, blocks);
     k_count_poly<true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(reinterpret_cast<const float*>(d_pairs), p);
+    if (cudaPeekAtLastError() != cudaSuccess) ctx->ticket_next = ticket_before;       // nothing ran: no ticket was drawn
     CU(ctx, cudaGetLastError());
     ctx->launches++;
     return SATMC_OK;

@@ -91,7 +91,22 @@ struct CountParams {
     // streamed
     const float* z; uint64_t ldz; uint64_t z_pair_stride; int ndof; int vec_ok;
     PhiloxKeys keys;           // fused: round keys, read straight from the constant bank
+    // dynamic work distribution (null = static grid-stride): a warp's first item is its global warp index, every further
+    // one is drawn from a device counter that only ever grows; ticket_base is its value when this launch starts
+    unsigned long long* ticket; unsigned long long ticket_base;
 };
+
+// Next work item of a warp.  `drawn` is the ticket lane 0 took while the warp was busy with the current item.
+__device__ __forceinline__ uint64_t next_item(const CountParams& p, uint64_t item, uint64_t stride, unsigned long long drawn)
+{
+    if (p.ticket == nullptr) return item + stride;
+    const unsigned long long t = __shfl_sync(0xffffffffu, drawn, 0);
+    return (uint64_t)(t - p.ticket_base) + stride;
+}
+__device__ __forceinline__ unsigned long long draw_ticket(const CountParams& p, int lane)
+{
+    return (p.ticket != nullptr && lane == 0) ? atomicAdd(p.ticket, 1ull) : 0ull;
+}
 
 // Slow, general evaluation of the slots of one sample group selected by slot_mask (bit t = sample
 // 4g+t): used for the ragged ends of a chunk and whenever the hot loop meets a sample the screening
@@ -280,8 +295,9 @@ __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED
     __shared__ unsigned s_part[kWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t stride = (uint64_t)gridDim.x * kWarps;
-    // items are laid out pair-major; with block_uniform all 8 warps of a block walk the loop in step
-    for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < p.n_items; item += stride) {
+    // items are laid out pair-major; with block_uniform all 8 warps of a block walk the loop in step (static order)
+    for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < p.n_items;) {
+        const unsigned long long drawn = draw_ticket(p, lane);       // in flight while this item is processed
         const uint64_t pair = item / p.n_chunks;
         const uint32_t chunk_id = (uint32_t)(item - pair * p.n_chunks);
         float v[12];
@@ -327,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED
                 atomicAdd(p.hits + pair, (unsigned long long)cnt);
             }
         }
+        item = next_item(p, item, stride, drawn);
     }
 }
 
@@ -612,7 +629,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_count_poly(const float* __restr
     __shared__ unsigned s_part[kWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t stride = (uint64_t)gridDim.x * kWarps;
-    for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < p.n_items; item += stride) {
+    for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < p.n_items;) {
+        const unsigned long long drawn = draw_ticket(p, lane);
         const uint64_t pair = item / p.n_chunks;
         const uint32_t chunk_id = (uint32_t)(item - pair * p.n_chunks);
         __syncwarp();
@@ -659,6 +677,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_count_poly(const float* __restr
                 atomicAdd(p.hits + pair, (unsigned long long)cnt);
             }
         }
+        item = next_item(p, item, stride, drawn);
     }
 }
 

@@ -379,6 +379,27 @@ def test_fused_sharding_invariance(ctx, dev, workloads):
     assert int(one[0]) == int(whole[5])
 
 
+def test_dynamic_work_distribution_is_invisible(ctx, dev, oracle, workloads):
+    """Launches with more items than resident warps draw their items from a device counter that is never reset (the host
+    mirrors it).  Counts must not depend on which warp got which item, nor on what ran before on the same context:
+    interleave statically scheduled launches (one pair over the whole GPU, the sweep) and ragged sizes, repeat, and
+    compare with the CPU restatement of the fused path."""
+    big = workloads.dataset_pairs(40_000, seed=611)                  # 40 000 items > 2 368 resident warps: tickets
+    five = workloads.dataset_pairs(30_001, seed=612, shape_variance=True)
+    first = fused(ctx, dev, big, 2_500, 31)
+    first5 = fused(ctx, dev, five, 1_027, 32, sample_offset=5)
+    sig = np.array([[0.1, 0.2, 0.3], [0.3, 0.1, 0.05]], np.float32)
+    d_sw = dev.zeros(64 * 2, np.uint64)
+    for rep in range(3):
+        fused(ctx, dev, big[:1], 3_000_000, 9)                       # block-uniform: static order, no tickets
+        ctx.count_fused_sweep(dev.put(big[:64]), 64, dev.put(sig.ravel()), 2, 10_000, 3, d_sw)
+        fused(ctx, dev, big[: 2_369 * (rep + 1)], 300, 8)            # just above / well above one item per warp
+        np.testing.assert_array_equal(fused(ctx, dev, big, 2_500, 31), first)
+        np.testing.assert_array_equal(fused(ctx, dev, five, 1_027, 32, sample_offset=5), first5)
+    for a, b in ((0, 40), (39_960, 40_000)):
+        np.testing.assert_array_equal(first[a:b], oracle.count_fused_batch(big[a:b], 2_500, 31, pair_id_offset=a))
+
+
 def test_fused_agrees_with_cpu_restatement_statistically(ctx, dev, oracle, workloads):
     """GPU sampler (MUFU) vs the oracle's libm restatement of the same sampler: normals agree to ~1e-6, so the
     counts differ only where a sample sits within ~1e-6 of the decision boundary: <= 3 per 1e5 samples."""
