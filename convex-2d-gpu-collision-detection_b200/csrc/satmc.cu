@@ -225,7 +225,9 @@ int satmc_exact_evals(satmc_ctx* ctx, uint64_t* out, int reset)
 // Chooses the chunking of the sample range (work item = (pair, chunk), one warp per item) and the grid size.
 // items_per_warp: how many items a resident warp should get at least (when the sample range allows); the static
 // grid-stride assignment loses up to 1/items_per_warp of the run to the last, partly filled round.
-static int plan_items(satmc_ctx* ctx, CountParams& p, int bps, uint64_t& blocks, int items_per_warp = 8)
+// max_chunk: upper bound on the samples of one item; 2^36 keeps the 32-bit per-lane counters exact (2^36 / 32 = 2^31).
+static int plan_items(satmc_ctx* ctx, CountParams& p, int bps, uint64_t& blocks, int items_per_warp = 8,
+                      uint64_t max_chunk = 1ull << 36)
 {
     const uint64_t resident_warps = (uint64_t)ctx->sm_count * bps * kWarps;
     const uint64_t target_items = resident_warps * (uint64_t)items_per_warp;
@@ -244,8 +246,8 @@ static int plan_items(satmc_ctx* ctx, CountParams& p, int bps, uint64_t& blocks,
             if (want > n_chunks) n_chunks = want;
         }
     }
-    const uint64_t max_chunk = 1ull << 36;                        // keeps the 32-bit per-lane counters exact (2^36 / 32 = 2^31)
-    if ((p.n_samples + n_chunks - 1) / n_chunks > max_chunk) n_chunks = (p.n_samples + max_chunk - 1) / max_chunk;
+    const uint64_t per_chunk = (p.n_samples + n_chunks - 1) / n_chunks;
+    if (per_chunk > max_chunk) n_chunks *= (per_chunk + max_chunk - 1) / max_chunk;   // a multiple: the rounds stay full
     if (n_chunks >= (uint64_t)kWarps) n_chunks = (n_chunks / kWarps) * kWarps;    // block-uniform pairs
     uint64_t chunk = (p.n_samples + n_chunks - 1) / n_chunks;
     chunk = ((chunk + 127) / 128) * 128;
@@ -295,8 +297,13 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
     if (tma) tma = make_z_tensor_map(&zmap, p.z, p.ldz, p.ndof);
     const int bps = tma ? ctx->blocks_per_sm_tma[p.ndof == 5] : (STREAMED ? ctx->blocks_per_sm_streamed : ctx->blocks_per_sm);
     uint64_t blocks = 0;
-    int rc = plan_items(ctx, p, bps, blocks);
+    // Long items (few pairs, many samples each -- cfg 4, cfg 5): undecided sample groups are queued per warp and worked
+    // off 32 at a time (ColdQueue, k_count<.., DEFER = true>).  Items are capped at 2^20 samples so that the queue holds an
+    // item's undecided groups at the rates seen in practice (<= 2.4e-4 per test).  Short items keep the immediate path:
+    // there the queue's bookkeeping costs more than the few undecided groups of an item.
+    int rc = plan_items(ctx, p, bps, blocks, 8, STREAMED ? (1ull << 36) : (1ull << 20));
     if (rc) return rc;
+    const bool defer = !STREAMED && p.chunk >= 32768;
     rc = clear_hits_for_atomics(ctx, p, p.n_pairs, p.flags);
     if (rc) return rc;
     const uint64_t ticket_before = ctx->ticket_next;
@@ -310,7 +317,8 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
         else
             k_count<Src, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
     } else {
-        k_count<Src, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
+        if (defer) k_count<Src, false, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
+        else k_count<Src, false, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
     }
     if (cudaPeekAtLastError() != cudaSuccess) ctx->ticket_next = ticket_before;       // nothing ran: no ticket was drawn
     CU(ctx, cudaGetLastError());

@@ -136,10 +136,35 @@ __device__ __noinline__ unsigned fused_group_slow(const PairConst& P, const floa
     return cnt;
 }
 
-// hot path: all four samples of group g
+// Deferred cold work of one warp.  A group the screening pass cannot decide is evaluated by ONE lane while the other
+// 31 wait (about 1 300 warp-instructions: regenerate the normals, screen again, precise sincos, 8-axis SAT).  Instead
+// of doing that on the spot the hot loop only records (output slot, group) here; the warp works the list off 32
+// entries at a time, all lanes busy, after an item or at the end of the kernel (cold_flush in k_count).
+constexpr unsigned kColdCap = 256;
+struct ColdQueue {
+    unsigned n;                   // entries pushed (may run past kColdCap: those were evaluated on the spot)
+    unsigned pair[kColdCap];      // output slot (index into hits / the live list)
+    uint64_t g[kColdCap];         // sample group
+};
+
+// rare branch of the hot loop: queue the group (contributes 0 now, its exact count is added by cold_flush) or, when
+// there is no queue (SATMC_EXACT_ONLY) or it is full, evaluate it here
 template <int D>
+__device__ __noinline__ unsigned fused_group_cold(ColdQueue* Q, unsigned pair_slot, const PairConst& Pcold, const float* robot,
+                                                  uint64_t g, uint32_t pid, const PhiloxKeys& K, unsigned long long* exact_evals)
+{
+    if (Q != nullptr) {
+        const unsigned slot = atomicAdd(&Q->n, 1u);
+        if (slot < kColdCap) { Q->pair[slot] = pair_slot; Q->g[slot] = g; return 0u; }
+    }
+    return fused_group_slow<D>(Pcold, robot, g, 0xFu, pid, K, exact_evals);
+}
+
+// hot path: all four samples of group g
+template <int D, bool DEFER>
 __device__ __forceinline__ unsigned fused_group(const PairConst& P, const PairConst& Pcold, const float* robot, uint64_t g,
-                                                uint32_t pid, const PhiloxKeys& K, unsigned long long* exact_evals)
+                                                uint32_t pid, const PhiloxKeys& K, unsigned long long* exact_evals,
+                                                ColdQueue* Q, unsigned pair_slot)
 {
     float n[4 * D];
     group_normals<D>((uint32_t)g, (uint32_t)(g >> 32), pid, K, n);
@@ -153,7 +178,9 @@ __device__ __forceinline__ unsigned fused_group(const PairConst& P, const PairCo
         cnt += __float_as_uint(m) >> 31;                            // m < 0 (m = -0 / NaN are undecided anyway)
         decided = decided && screen_decided<D>(P, m, hmin);
     }
-    if (!decided) cnt = fused_group_slow<D>(Pcold, robot, g, 0xFu, pid, K, exact_evals);   // rare: redo the group
+    if (!decided)                                                   // rare: redo the group, now or (DEFER) in cold_flush
+        cnt = DEFER ? fused_group_cold<D>(Q, pair_slot, Pcold, robot, g, pid, K, exact_evals)
+                    : fused_group_slow<D>(Pcold, robot, g, 0xFu, pid, K, exact_evals);
     return cnt;
 }
 
@@ -180,10 +207,10 @@ __device__ __noinline__ unsigned streamed_sample(const PairConst& P, const float
 // ragged groups at the ends through the slow path on lanes 0 and 1
 // P lives in registers for the hot loop; Pcold is the same data in shared memory, handed to the out-of-line
 // cold functions so that P's address is never taken (otherwise the compiler homes P on the local stack).
-template <int D>
+template <int D, bool DEFER>
 __device__ __forceinline__ unsigned fused_chunk(const PairConst& P, const PairConst& Pcold, const float* robot, uint64_t b,
                                                 uint64_t e, uint32_t pid, const PhiloxKeys& K, int lane,
-                                                unsigned long long* exact_evals)
+                                                unsigned long long* exact_evals, ColdQueue* Q, unsigned pair_slot)
 {
     unsigned cnt = 0;
     const uint64_t g_lo = (b + 3) >> 2, g_hi = e >> 2;
@@ -195,7 +222,7 @@ __device__ __forceinline__ unsigned fused_chunk(const PairConst& P, const PairCo
         return cnt;
     }
     for (uint64_t g = g_lo + (uint64_t)lane; g < g_hi; g += 32)
-        cnt += fused_group<D>(P, Pcold, robot, g, pid, K, exact_evals);
+        cnt += fused_group<D, DEFER>(P, Pcold, robot, g, pid, K, exact_evals, Q, pair_slot);
     if (lane == 0 && (b & 3))
         cnt += fused_group_slow<D>(Pcold, robot, b >> 2, (0xFu << (unsigned)(b & 3)) & 0xFu, pid, K, exact_evals);
     if (lane == 1 && (e & 3))
@@ -287,14 +314,46 @@ __device__ __forceinline__ unsigned streamed_chunk(const PairConst& P, const Pai
     return cnt;
 }
 
-template <class Src, bool STREAMED>
+// Works off the warp's deferred groups, one entry per lane: rebuild the pair's constants, evaluate the group with the
+// same code the immediate path uses, add the count to the pair's counter.  Entries may belong to earlier items of
+// this warp; their counters were stored before (plain store or atomic, ordered by __syncwarp), so an atomic add is right.
+template <class Src>
+__device__ __noinline__ void cold_flush(ColdQueue* Qp, const Src& src, const CountParams& p, int lane)
+{
+    ColdQueue& Q = *Qp;
+    __syncwarp();
+    const unsigned n = Q.n < kColdCap ? Q.n : kColdCap;
+    for (unsigned i = (unsigned)lane; i < n; i += 32) {
+        const unsigned slot = Q.pair[i];
+        const uint64_t g = Q.g[i];
+        float v[12];
+        const uint64_t elem = src.element(slot);
+        src.load(elem, v);
+        PairConst P;
+        pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
+        float robot[8];
+        exact_robot_corners(v[0], v[1], P.ca, P.sa, v[3], v[4], robot);
+        const uint32_t pid = p.pair_id_offset + (uint32_t)elem;
+        const unsigned c = (v[10] == 0.0f && v[11] == 0.0f) ? fused_group_slow<3>(P, robot, g, 0xFu, pid, p.keys, p.exact_evals)
+                                                           : fused_group_slow<5>(P, robot, g, 0xFu, pid, p.keys, p.exact_evals);
+        if (c) atomicAdd(p.hits + slot, (unsigned long long)c);
+    }
+    __syncwarp();
+    if (lane == 0) Q.n = 0;
+    __syncwarp();
+}
+
+template <class Src, bool STREAMED, bool DEFER = false>
 __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED : SATMC_MIN_BLOCKS_FUSED) k_count(const __grid_constant__ Src src, const __grid_constant__ CountParams p)
 {
     __shared__ float s_robot[kWarps][8];
     __shared__ PairConst s_pair[kWarps];
     __shared__ unsigned s_part[kWarps];
+    __shared__ ColdQueue s_cold[DEFER ? kWarps : 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t stride = (uint64_t)gridDim.x * kWarps;
+    ColdQueue* const Q = (!DEFER || (p.flags & SATMC_EXACT_ONLY)) ? nullptr : &s_cold[DEFER ? warp : 0];
+    if (DEFER && Q != nullptr) { if (lane == 0) Q->n = 0; __syncwarp(); }
     // items are laid out pair-major; with block_uniform all 8 warps of a block walk the loop in step (static order)
     for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < p.n_items;) {
         const unsigned long long drawn = draw_ticket(p, lane);       // in flight while this item is processed
@@ -322,8 +381,8 @@ __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED
             const uint32_t pid = p.pair_id_offset + (uint32_t)elem;
             const uint64_t s_begin = p.sample_offset + c_begin;
             const bool dof3 = (v[10] == 0.0f) && (v[11] == 0.0f);
-            cnt = dof3 ? fused_chunk<3>(P, Pc, s_robot[warp], s_begin, s_begin + c_len, pid, p.keys, lane, ev)
-                       : fused_chunk<5>(P, Pc, s_robot[warp], s_begin, s_begin + c_len, pid, p.keys, lane, ev);
+            cnt = dof3 ? fused_chunk<3, DEFER>(P, Pc, s_robot[warp], s_begin, s_begin + c_len, pid, p.keys, lane, ev, Q, (unsigned)pair)
+                       : fused_chunk<5, DEFER>(P, Pc, s_robot[warp], s_begin, s_begin + c_len, pid, p.keys, lane, ev, Q, (unsigned)pair);
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (p.block_uniform) {
@@ -343,8 +402,13 @@ __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED
                 atomicAdd(p.hits + pair, (unsigned long long)cnt);
             }
         }
+        if (DEFER && Q != nullptr) {
+            __syncwarp();
+            if (Q->n >= 32u) cold_flush(Q, src, p, lane);            // enough for a full pass
+        }
         item = next_item(p, item, stride, drawn);
     }
+    if (DEFER && Q != nullptr) cold_flush(Q, src, p, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
