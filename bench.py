@@ -38,12 +38,14 @@ PKG = "convex-2d-gpu-collision-detection_b200"
 METRIC = "SAT pair-tests/sec"
 UNIT = "tests/s"
 # Issue cost of one test in the fused 3-DoF loop, read off the SASS of k_count: per 4-sample
-# group 332 instructions, 60 of them IMAD.WIDE.  On sm_100a an IMAD.WIDE holds the warp scheduler's issue port for
-# ~4 cycles and does not overlap with FP32 issue (tools/ubench.cu: "IMAD.WIDE+LOP3+4 FFMA" = 9.4 clk, purely additive;
-# profiles/r1_ubench.log), so a group costs 272 + 60*4 = 512 issue slots = 128 lane-slots per test.
-ISSUE_SLOTS_PER_TEST = 128.0
-# FMA-pipe view of the same loop: 124 FP32 + 60 IMAD.WIDE x 4 = 364 FFMA-equivalent slots per group -> 91 per test
-FMA_SLOTS_PER_TEST = 91.0
+# group 337 instructions, 53 of them IMAD.WIDE (the loop-invariant Philox products are hoisted).  On sm_100a an IMAD.WIDE
+# holds the warp scheduler's issue port for ~4 cycles and does not overlap with FP32 issue (tools/ubench.cu:
+# "IMAD.WIDE+LOP3+4 FFMA" = 9.4 clk, purely additive; profiles/r1_ubench.log), so a group costs 284 + 53*4 = 496 issue
+# slots = 124 lane-slots per test.
+ISSUE_SLOTS_PER_TEST = 124.0
+INSTR_PER_TEST = 337.0 / 4.0     # plain count, every instruction one slot: what ncu's issue-active measures
+# FMA-pipe view of the same loop: 124 FP32 + 53 IMAD.WIDE x 4 = 336 FFMA-equivalent slots per group -> 84 per test
+FMA_SLOTS_PER_TEST = 84.0
 SURVEY_I_FMA_W8 = 247.0      # 8-axis kernel, 3-DoF
 SURVEY_I_FMA_W4 = 163.0      # 4-axis kernel (+ exact fallback), 3-DoF
 
@@ -317,13 +319,15 @@ def main():
                 "achieved": per_gpu * ISSUE_SLOTS_PER_TEST / 1e12, "peak": fma_peak / 1e12, "unit": "T lane-issue-slots/s",
                 "frac": per_gpu * ISSUE_SLOTS_PER_TEST / fma_peak, "traffic": 4.86e6,
                 "peak_source": f"148 SM x 4 schedulers x 32 lanes x sm_max_mhz {sm_mhz:.0f} from {src} (= the FP32 lane peak)",
-                "alg_units": "128 issue slots per test: per 4-sample group 272 single-slot instructions + 60 IMAD.WIDE x 4 slots "
+                "alg_units": "124 issue slots per test: per 4-sample group 284 single-slot instructions + 53 IMAD.WIDE x 4 slots "
                              "(IMAD.WIDE blocks issue ~4 clk on sm_100a, profiles/r1_ubench.log)",
+                "frac_issue_plain": per_gpu * INSTR_PER_TEST / fma_peak,
                 "frac_fma_pipe": per_gpu * FMA_SLOTS_PER_TEST / fma_peak,
                 "frac_vs_survey_w8_model": per_gpu * SURVEY_I_FMA_W8 / fma_peak,
                 "frac_vs_survey_w4_model": per_gpu * SURVEY_I_FMA_W4 / fma_peak,
-                "note": "frac = issue-slot utilisation on this kernel's own SASS count; frac_fma_pipe counts only FMA-pipe work "
-                        "(124 FP32 + 60 IMAD.WIDE x4 per group); the last two are against SURVEY.md 8(d)'s instruction models "
+                "note": "frac = issue-slot utilisation on this kernel's own SASS count with IMAD.WIDE weighted 4; frac_issue_plain "
+                        "weights every instruction 1 (= ncu's issue-active); frac_fma_pipe counts only FMA-pipe work "
+                        "(124 FP32 + 53 IMAD.WIDE x4 per group); the last two are against SURVEY.md 8(d)'s instruction models "
                         "(247 / 163 FMA-pipe instructions per test) and exceed 1 because the screening pass needs ~46",
             },
             "hits_checksum": hits_total,

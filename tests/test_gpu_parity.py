@@ -400,6 +400,31 @@ def test_dynamic_work_distribution_is_invisible(ctx, dev, oracle, workloads):
         np.testing.assert_array_equal(first[a:b], oracle.count_fused_batch(big[a:b], 2_500, 31, pair_id_offset=a))
 
 
+def test_deferred_cold_groups_long_items(ctx, dev, oracle, satmc, workloads):
+    """Items of >= 32 768 samples run the variant that queues undecided groups per warp and evaluates them 32 at a time.
+    Its counts must equal the all-exact evaluation (no queue) for a pair with the usual undecided rate, a pair whose
+    every sample is undecided (the queue overflows and falls back to evaluation on the spot) and a pair that never
+    queues anything; and the CPU restatement on a sample range that straddles an item boundary."""
+    base = workloads.cfg2_pair()
+    near = satmc.pairs_from_columns((4.07 + 2.3) / 2, 0.1, 0.0, 2.3, 1.1, 3e-6, 3e-6, 2e-6)      # face-to-face contact
+    far = base.copy(); far["rx"] = 40.0
+    pairs = np.concatenate([base, near, far])
+    n = 220_000_000                                                   # 3 pairs -> 6 312 chunks of 34 944 samples
+    ctx.exact_evals(reset=True)
+    fast = fused(ctx, dev, pairs, n, 77)
+    deferred_evals = ctx.exact_evals(reset=True)
+    exact = fused(ctx, dev, pairs, n, 77, flags=EXACT)
+    np.testing.assert_array_equal(fast, exact)
+    assert 0 < fast[0] < n and 0 < fast[1] < n and fast[2] == 0
+    assert deferred_evals > 0.5 * n                                   # the near pair really went through the cold path
+    # one pair alone (every warp of a block on the same pair, block reduction + queue), odd offset
+    one = fused(ctx, dev, base, 700_000_001, 78, sample_offset=3)
+    np.testing.assert_array_equal(one, fused(ctx, dev, base, 700_000_001, 78, sample_offset=3, flags=EXACT))
+    lo = 34_944 * 5 - 1000
+    part = fused(ctx, dev, pairs[:2], 2_000, 77, sample_offset=lo)
+    np.testing.assert_array_equal(part, oracle.count_fused_batch(pairs[:2], 2_000, 77, sample_offset=lo))
+
+
 def test_fused_agrees_with_cpu_restatement_statistically(ctx, dev, oracle, workloads):
     """GPU sampler (MUFU) vs the oracle's libm restatement of the same sampler: normals agree to ~1e-6, so the
     counts differ only where a sample sits within ~1e-6 of the decision boundary: <= 3 per 1e5 samples."""
