@@ -28,12 +28,19 @@ struct satmc_ctx {
     char err[512] = {0};
     uint64_t launches = 0;
     unsigned long long* d_exact_evals = nullptr;
-    unsigned long long* d_ticket = nullptr;  // work-item counter of the dynamically scheduled kernels: never reset,
-    uint64_t ticket_next = 0;                // the host mirrors its value (every processed item draws exactly one ticket)
+    // work-item counters of the dynamically scheduled kernels: never reset, the host mirrors their values (every processed
+    // item draws exactly one ticket).  Two of them: launches on the auxiliary stream (pipelined host calls) may run
+    // concurrently with launches on the main stream and must not share a counter.
+    unsigned long long* d_ticket = nullptr;
+    uint64_t ticket_next[2] = {0, 0};
+    int ticket_sel = 0;
+    cudaStream_t aux = nullptr;              // pipelined host calls: second slice (created on first use)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
     bool last_ms_valid = false;
+    bool events_by_caller = false;           // a pipelined host call brackets both of its launches itself
     // grow-only device scratch
     void* d_scratch[3] = {nullptr, nullptr, nullptr};
     size_t scratch_cap[3] = {0, 0, 0};
@@ -155,8 +162,8 @@ int satmc_create(int device, void* stream, satmc_ctx** out)
     cudaGetLastError();
     if (cudaMalloc(&ctx->d_exact_evals, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(ctx->d_exact_evals, 0, sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMalloc(&ctx->d_ticket, sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(ctx->d_ticket, 0, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(ctx->d_ticket, 0, 2 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
         int rc = fail(nullptr, SATMC_ERR_CUDA, "context allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete ctx;
@@ -174,6 +181,9 @@ int satmc_destroy(satmc_ctx* ctx)
     for (int i = 0; i < 3; i++) if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
     if (ctx->d_exact_evals) cudaFree(ctx->d_exact_evals);
     if (ctx->d_ticket) cudaFree(ctx->d_ticket);
+    if (ctx->aux) cudaStreamDestroy(ctx->aux);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     delete ctx;
@@ -268,9 +278,9 @@ static int plan_items(satmc_ctx* ctx, CountParams& p, int bps, uint64_t& blocks,
 static void use_tickets(satmc_ctx* ctx, CountParams& p, uint64_t blocks)
 {
     if (p.block_uniform || p.n_items <= blocks * (uint64_t)kWarps) return;
-    p.ticket = ctx->d_ticket;
-    p.ticket_base = ctx->ticket_next;
-    ctx->ticket_next += p.n_items;
+    p.ticket = ctx->d_ticket + ctx->ticket_sel;
+    p.ticket_base = ctx->ticket_next[ctx->ticket_sel];
+    ctx->ticket_next[ctx->ticket_sel] += p.n_items;
 }
 
 // With several chunks per pair the kernels accumulate with atomics: the counters must start from zero unless the
@@ -306,9 +316,9 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
     const bool defer = !STREAMED && p.chunk >= 32768;
     rc = clear_hits_for_atomics(ctx, p, p.n_pairs, p.flags);
     if (rc) return rc;
-    const uint64_t ticket_before = ctx->ticket_next;
+    const uint64_t ticket_before = ctx->ticket_next[ctx->ticket_sel];
     if (!tma) use_tickets(ctx, p, blocks);
-    if (time_it) CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if (time_it && !ctx->events_by_caller) CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if constexpr (STREAMED) {
         if (tma && p.ndof == 5)
             k_count_streamed_tma<5><<<(unsigned)blocks, kThreads, tma_smem_bytes(5), ctx->stream>>>(src, p, zmap);
@@ -320,9 +330,9 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
         if (defer) k_count<Src, false, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
         else k_count<Src, false, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
     }
-    if (cudaPeekAtLastError() != cudaSuccess) ctx->ticket_next = ticket_before;       // nothing ran: no ticket was drawn
+    if (cudaPeekAtLastError() != cudaSuccess) ctx->ticket_next[ctx->ticket_sel] = ticket_before;       // nothing ran: no ticket was drawn
     CU(ctx, cudaGetLastError());
-    if (time_it) { CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream)); ctx->last_ms_valid = true; }
+    if (time_it && !ctx->events_by_caller) { CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream)); ctx->last_ms_valid = true; }
     ctx->launches++;
     return SATMC_OK;
 }
@@ -467,10 +477,10 @@ int satmc_count_fused_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs, u
     if (rc) return rc;
     rc = clear_hits_for_atomics(ctx, p, n_pairs, flags);
     if (rc) return rc;
-    const uint64_t ticket_before = ctx->ticket_next;
+    const uint64_t ticket_before = ctx->ticket_next[ctx->ticket_sel];
     use_tickets(ctx, p, blocks);
     k_count_poly<false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(reinterpret_cast<const float*>(d_pairs), p);
-    if (cudaPeekAtLastError() != cudaSuccess) ctx->ticket_next = ticket_before;       // nothing ran: no ticket was drawn
+    if (cudaPeekAtLastError() != cudaSuccess) ctx->ticket_next[ctx->ticket_sel] = ticket_before;       // nothing ran: no ticket was drawn
     CU(ctx, cudaGetLastError());
     ctx->launches++;
     return SATMC_OK;
@@ -495,10 +505,10 @@ int satmc_count_streamed_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs
     if (rc) return rc;
     rc = clear_hits_for_atomics(ctx, p, n_pairs, flags);
     if (rc) return rc;
-    const uint64_t ticket_before = ctx->ticket_next;
+    const uint64_t ticket_before = ctx->ticket_next[ctx->ticket_sel];
     use_tickets(ctx, p, blocks);
     k_count_poly<true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(reinterpret_cast<const float*>(d_pairs), p);
-    if (cudaPeekAtLastError() != cudaSuccess) ctx->ticket_next = ticket_before;       // nothing ran: no ticket was drawn
+    if (cudaPeekAtLastError() != cudaSuccess) ctx->ticket_next[ctx->ticket_sel] = ticket_before;       // nothing ran: no ticket was drawn
     CU(ctx, cudaGetLastError());
     ctx->launches++;
     return SATMC_OK;
@@ -721,16 +731,65 @@ int satmc_write_collision_probability(satmc_ctx* ctx, float* d_counts, int n_don
 
 // ---- host-buffer variants ---------------------------------------------------------------------
 
+// Large batches from host memory in two slices: a lead slice of one item per planned work item (18 944 pairs) on the
+// context's stream, the rest on an auxiliary stream.  The rest's host->device copy runs under the lead kernel, the
+// lead's counters go back under the second kernel, and the second kernel's blocks move in as the lead's retire, so
+// only the lead's copy in and the rest's copy out remain exposed.
+static int count_fused_host_pipelined(satmc_ctx* ctx, const satmc_pair* h_pairs, uint64_t n_pairs, uint64_t lead,
+                                      uint64_t n_samples, uint64_t seed, uint64_t sample_offset, uint32_t pair_id_offset,
+                                      uint64_t* h_hits, uint32_t flags, satmc_pair* d_pairs, uint64_t* d_hits)
+{
+    if (!ctx->aux) {
+        CU(ctx, cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+        CU(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        CU(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
+    cudaStream_t A = ctx->stream, B = ctx->aux;
+    const uint64_t rest = n_pairs - lead;
+    CU(ctx, cudaEventRecord(ctx->ev_fork, A));                       // the call stays ordered after earlier work on A
+    CU(ctx, cudaStreamWaitEvent(B, ctx->ev_fork, 0));
+    CU(ctx, cudaMemcpyAsync(d_pairs, h_pairs, lead * sizeof(satmc_pair), cudaMemcpyHostToDevice, A));
+    if (flags & SATMC_ACCUMULATE) CU(ctx, cudaMemcpyAsync(d_hits, h_hits, lead * sizeof(uint64_t), cudaMemcpyHostToDevice, A));
+    CU(ctx, cudaMemcpyAsync(d_pairs + lead, h_pairs + lead, rest * sizeof(satmc_pair), cudaMemcpyHostToDevice, B));
+    if (flags & SATMC_ACCUMULATE)
+        CU(ctx, cudaMemcpyAsync(d_hits + lead, h_hits + lead, rest * sizeof(uint64_t), cudaMemcpyHostToDevice, B));
+    ctx->events_by_caller = true;
+    CU(ctx, cudaEventRecord(ctx->ev0, A));
+    int rc = satmc_count_fused(ctx, d_pairs, lead, n_samples, seed, sample_offset, pair_id_offset, d_hits, flags);
+    if (rc == SATMC_OK) {
+        cudaMemcpyAsync(h_hits, d_hits, lead * sizeof(uint64_t), cudaMemcpyDeviceToHost, A);
+        ctx->stream = B; ctx->ticket_sel = 1;
+        rc = satmc_count_fused(ctx, d_pairs + lead, rest, n_samples, seed, sample_offset, pair_id_offset + (uint32_t)lead,
+                               d_hits + lead, flags);
+        ctx->stream = A; ctx->ticket_sel = 0;
+    }
+    ctx->events_by_caller = false;
+    if (rc == SATMC_OK) cudaMemcpyAsync(h_hits + lead, d_hits + lead, rest * sizeof(uint64_t), cudaMemcpyDeviceToHost, B);
+    cudaEventRecord(ctx->ev_join, B);                                // always rejoin, also after an error
+    cudaStreamWaitEvent(A, ctx->ev_join, 0);
+    cudaEventRecord(ctx->ev1, A);
+    ctx->last_ms_valid = (rc == SATMC_OK);
+    if (rc) { cudaStreamSynchronize(A); return rc; }
+    CU(ctx, cudaStreamSynchronize(A));
+    CU(ctx, cudaGetLastError());
+    return SATMC_OK;
+}
+
 int satmc_count_fused_host(satmc_ctx* ctx, const satmc_pair* h_pairs, uint64_t n_pairs, uint64_t n_samples, uint64_t seed,
                            uint64_t sample_offset, uint32_t pair_id_offset, uint64_t* h_hits, uint32_t flags)
 {
     if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
     if ((!h_pairs || !h_hits) && n_pairs) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
     if (n_pairs == 0) return SATMC_OK;
+    if (n_pairs > 0xffffffffull - pair_id_offset) return fail(ctx, SATMC_ERR_INVALID, "pair ids exceed 32 bits");
     DeviceGuard g(ctx->device);
     void *d_pairs = nullptr, *d_hits = nullptr;
     int rc = scratch(ctx, 1, n_pairs * sizeof(satmc_pair), &d_pairs); if (rc) return rc;
     rc = scratch(ctx, 2, n_pairs * sizeof(uint64_t), &d_hits); if (rc) return rc;
+    const uint64_t lead = (uint64_t)ctx->sm_count * ctx->blocks_per_sm * kWarps * 8;     // = plan_items' target: one chunk per pair
+    if (n_samples > 0 && n_pairs >= 2 * lead)
+        return count_fused_host_pipelined(ctx, h_pairs, n_pairs, lead, n_samples, seed, sample_offset, pair_id_offset, h_hits,
+                                          flags, (satmc_pair*)d_pairs, (uint64_t*)d_hits);
     CU(ctx, cudaMemcpyAsync(d_pairs, h_pairs, n_pairs * sizeof(satmc_pair), cudaMemcpyHostToDevice, ctx->stream));
     if (flags & SATMC_ACCUMULATE)
         CU(ctx, cudaMemcpyAsync(d_hits, h_hits, n_pairs * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));

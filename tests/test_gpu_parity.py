@@ -583,6 +583,24 @@ def test_host_entry_points(ctx, dev, oracle, workloads):
     assert ctx.last_kernel_ms() > 0
 
 
+def test_host_call_in_two_slices(ctx, dev, workloads):
+    """From 2 x 18 944 pairs on, satmc_count_fused_host runs a lead slice on the context's stream and the rest on an
+    auxiliary stream (copies under compute, two kernels drawing from separate ticket counters): the counts must be the
+    ones of the plain device call, also when accumulating and after other launches in between."""
+    pairs = workloads.dataset_pairs(50_001, seed=23)
+    want = fused(ctx, dev, pairs, 700, 12, sample_offset=9, pair_id_offset=5)
+    for rep in range(3):
+        got = ctx.count_fused_host(pairs, 700, 12, sample_offset=9, pair_id_offset=5)
+        np.testing.assert_array_equal(got, want)
+        assert ctx.last_kernel_ms() > 0
+        fused(ctx, dev, pairs[:3000 * (rep + 1)], 333, 4)              # main-stream tickets advance in between
+    acc = want.copy()
+    ctx.count_fused_host(pairs, 700, 12, sample_offset=709, pair_id_offset=5, flags=ACC, out=acc)
+    np.testing.assert_array_equal(acc, fused(ctx, dev, pairs, 1400, 12, sample_offset=9, pair_id_offset=5))
+    five = workloads.dataset_pairs(40_000, seed=24, shape_variance=True)
+    np.testing.assert_array_equal(ctx.count_fused_host(five, 300, 13), fused(ctx, dev, five, 300, 13))
+
+
 def test_argument_errors(ctx, dev, satmc, workloads):
     pairs = workloads.dataset_pairs(4, seed=1)
     z = workloads.normal_bank(64, 3, seed=1)
