@@ -58,6 +58,9 @@ __global__ void __launch_bounds__(1024, 1) k(uint32_t seed, uint32_t* sink, long
                                 x = fmaxf(fmaxf(y, z), fmaxf(w, v)); }
                 f[i] = x;
             }
+            if (OP == 24) { f[i] = fmaf(f[i], f[(i + 1) % ILP], f[(i + 3) % ILP]); }                                         // FFMA, three register sources
+            if (OP == 25) { f[i] = fmaf(f[i], f[(i + 1) % ILP], 1e-9f); }                                                   // FFMA, two register sources
+            if (OP == 26) { f[i] = fmaf(f[(i + 2) % ILP], f[(i + 1) % ILP], f[(i + 3) % ILP]) + f[i] * 1e-9f; }              // FFMA 3 regs (dst != src) + FFMA
             if (OP == 16) { a[i] = __float_as_uint(f[i] = fmaf(f[i], 1.0000001f, 1e-9f)) >> 31; }                           // FFMA + SHF
         }
     }
@@ -69,24 +72,37 @@ __global__ void __launch_bounds__(1024, 1) k(uint32_t seed, uint32_t* sink, long
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+static int g_threads = 1024;
+
 template <int OP> void run(const char* name, int instr_per_op)
 {
     int sms = 148;
     uint32_t* sink; long long* cyc;
     cudaMalloc(&sink, sms * 1024 * 4); cudaMalloc(&cyc, sms * 8);
-    k<OP><<<sms, 1024>>>(12345u, sink, cyc);
-    k<OP><<<sms, 1024>>>(12345u, sink, cyc);
+    k<OP><<<sms, g_threads>>>(12345u, sink, cyc);
+    k<OP><<<sms, g_threads>>>(12345u, sink, cyc);
     cudaDeviceSynchronize();
     long long h[148]; cudaMemcpy(h, cyc, sms * 8, cudaMemcpyDeviceToHost);
     double avg = 0; for (int i = 0; i < sms; i++) avg += h[i]; avg /= sms;
-    double warp_ops = 32.0 * ITERS * ILP;            // per SM: 32 warps
+    double warp_ops = (g_threads / 32.0) * ITERS * ILP;            // per SM: g_threads / 32 warps
     printf("%-28s %8.1f cyc  %6.3f ops/clk/SM (=%5.2f per SMSP)  ~%.3f warp-instr/clk/SM\n", name, avg, warp_ops / avg, warp_ops / avg / 4,
            warp_ops * instr_per_op / avg);
     cudaFree(sink); cudaFree(cyc);
 }
 
-int main()
+int main(int argc, char** argv)
 {
+    if (argc > 2) {                      // register-operand probe
+        run<3>("FFMA r,imm,imm", 1); run<25>("FFMA r,r,imm", 1); run<24>("FFMA r,r,r", 1); run<26>("FFMA r,r,r + FFMA r,imm,r", 2);
+        return 0;
+    }
+    if (argc > 1) {                      // occupancy probe: the screening mixes at fewer resident warps per scheduler
+        for (int t : {1024, 768, 512, 384, 256, 128}) {
+            g_threads = t; printf("-- %d warps per scheduler\n", t / 128);
+            run<20>("16 FFMA", 16); run<22>("14 FFMA + SIN + COS", 18); run<23>("8 FFMA+4 FADD+3 FMNMX+SIN+COS", 19);
+        }
+        return 0;
+    }
     run<3>("FFMA", 1); run<11>("FADD", 1); run<1>("IMAD", 1); run<0>("IMAD.WIDE+LOP3", 2); run<7>("IMAD.WIDE+IADD3", 2); run<2>("LOP3(x2)", 2);
     run<12>("I2F.U32+LOP3", 2); run<13>("IMAD.HI", 1); run<14>("IMAD.WIDE(+c)", 1); run<15>("MUFU.SQRT", 1);
     run<19>("4 FFMA", 4); run<17>("IMAD.WIDE+LOP3+4 FFMA", 6); run<18>("IMAD.WIDE+LOP3+8 FFMA", 10);
