@@ -571,6 +571,34 @@ def test_mc_step_matches_oracle_tail(ctx, dev, oracle, workloads):
     np.testing.assert_array_equal(dev.get(d_cps), total.astype(np.float32) / np.float32(3 * n_batch))
 
 
+def test_mc_step_long_batch_deferred_path(ctx, dev, workloads):
+    """The reference kernel signature with one huge batch for two slots: items of >= 32 768 samples take the variant with
+    the deferred cold queue, reading the pair through the index tables.  Same counts as the direct call (hits stay
+    below 2^24, so the reference's float counter is exact)."""
+    pairs = np.repeat(workloads.cfg2_pair(), 2)
+    pairs["rx"][1] = 40.0                                              # never collides
+    for rx in np.arange(3.6, 6.0, 0.1):                                # push the first one out until p ~ 1e-3 .. 1e-2
+        pairs["rx"][0] = rx
+        p_est = int(fused(ctx, dev, pairs[:1], 1_000_000, 1)[0]) / 1e6
+        if p_est < 8e-3:
+            break
+    assert p_est > 1e-4
+    robot_base, poses, sds, pi, si, pos = workloads.reference_tables(pairs)
+    bins = np.array([0, 0.01, 0.1, 1.0], np.float32); acc = np.zeros(3, np.float32)
+    d = {k: dev.put(v) for k, v in dict(rb=robot_base, poses=poses.ravel(), sds=sds.ravel(), pi=pi, si=si,
+                                        pos=pos.ravel(), bins=bins, acc=acc).items()}
+    d_cps = dev.zeros(2, np.float32); d_done = dev.zeros(2, np.int32)
+    n = 1_000_000_000
+    ctx.exact_evals(reset=True)
+    ctx.mc_step(d["rb"], d["poses"], 2, d["sds"], 2, d["pi"], d["si"], d["pos"], d_cps, d["bins"], d["acc"], 4, d_done,
+                0, n, n, 2, 57, 3)
+    ctx.synchronize()
+    assert ctx.exact_evals() > 1000
+    want = fused(ctx, dev, pairs, n, 57, pair_id_offset=3, flags=EXACT)
+    assert 0 < want[0] < 2 ** 24 and want[1] == 0
+    np.testing.assert_array_equal(dev.get(d_cps).astype(np.int64), want.astype(np.int64))
+
+
 # ---- host-buffer entry points ---------------------------------------------------------------------------
 def test_host_entry_points(ctx, dev, oracle, workloads):
     pairs = workloads.dataset_pairs(257, seed=19)
