@@ -34,6 +34,7 @@ struct satmc_ctx {
     unsigned long long* d_ticket = nullptr;
     uint64_t ticket_next[2] = {0, 0};
     int ticket_sel = 0;
+    SweepPlan* d_sweep_plan = nullptr;       // written by k_sweep_plan, read by both k_count_sweep variants
     cudaStream_t aux = nullptr;              // pipelined host calls: second slice (created on first use)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool profiling = false;
@@ -162,6 +163,7 @@ int satmc_create(int device, void* stream, satmc_ctx** out)
     cudaGetLastError();
     if (cudaMalloc(&ctx->d_exact_evals, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(ctx->d_exact_evals, 0, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_sweep_plan, sizeof(SweepPlan)) != cudaSuccess ||
         cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(ctx->d_ticket, 0, 2 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
@@ -181,6 +183,7 @@ int satmc_destroy(satmc_ctx* ctx)
     for (int i = 0; i < 3; i++) if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
     if (ctx->d_exact_evals) cudaFree(ctx->d_exact_evals);
     if (ctx->d_ticket) cudaFree(ctx->d_ticket);
+    if (ctx->d_sweep_plan) cudaFree(ctx->d_sweep_plan);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -543,9 +546,13 @@ int satmc_count_fused_sweep(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t 
         const int nc = (int)((n_cov - c0 < (uint32_t)kSweepMax) ? n_cov - c0 : kSweepMax);
         CountParams q = p;
         q.hits = p.hits + c0;
-        k_count_sweep<<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(d_pairs, d_sigmas + 3 * (size_t)c0, nc, (uint64_t)n_cov, q);
+        k_sweep_plan<<<1, kSweepMax, 0, ctx->stream>>>(d_sigmas + 3 * (size_t)c0, nc, ctx->d_sweep_plan);
+        k_count_sweep<false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(d_pairs, d_sigmas + 3 * (size_t)c0, nc, (uint64_t)n_cov, q,
+                                                                            ctx->d_sweep_plan);
+        k_count_sweep<true><<<(unsigned)blocks, 32 * sweep_warps(true), 0, ctx->stream>>>(d_pairs, d_sigmas + 3 * (size_t)c0, nc, (uint64_t)n_cov, q,
+                                                                           ctx->d_sweep_plan);
         CU(ctx, cudaGetLastError());
-        ctx->launches++;
+        ctx->launches += 3;
     }
     return SATMC_OK;
 }

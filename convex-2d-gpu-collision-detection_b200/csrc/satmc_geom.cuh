@@ -190,14 +190,21 @@ __device__ __forceinline__ void pair_const_init(PairConst& P, float rx, float ry
 // screening pass: largest normalised signed gap over the 4 box axes (m > 0 separated, m < 0 overlap)
 // 22 FP32 instructions + 2 MUFU per sample (3-DoF)
 // ---------------------------------------------------------------------------------------------
+// The screening value in two steps, so that callers evaluating one sample under several settings with the same
+// sd_theta can keep the trigonometric part (covariance sweep).  screen_gap is exactly screen_trig + screen_gap_sc.
+__device__ __forceinline__ void screen_trig(float nst, float th, float z2, float& s, float& c)
+{
+    // relative angle phi = theta - dt of the robot frame against the sampled obstacle frame
+    const float phi = fmaf(nst, z2, th);
+    s = __sinf(phi); c = __cosf(phi);
+}
+
 template <int NDOF>
-__device__ __forceinline__ float screen_gap(const PairConst& P, float z0, float z1, float z2, float z3, float z4,
-                                            float& hmin)
+__device__ __forceinline__ float screen_gap_sc(const PairConst& P, float z0, float z1, float s, float c, float z3, float z4,
+                                               float& hmin)
 {
     // u in the robot frame, then rotated by the relative angle phi = theta - dt into the obstacle frame:
     // u.B0 = cos(phi) u.A0 - sin(phi) u.A1,  u.B1 = sin(phi) u.A0 + cos(phi) u.A1;  |A_i.B_j| = |cos phi|, |sin phi|
-    const float phi = fmaf(P.nst, z2, P.th);
-    const float s = __sinf(phi), c = __cosf(phi);
     const float ua0 = fmaf(P.nkx0, z0, fmaf(P.nky0, z1, P.pa0));
     const float ua1 = fmaf(P.kx1, z0, fmaf(P.nky1, z1, P.pa1));
     const float ub0 = fmaf(c, ua0, -(s * ua1));
@@ -213,6 +220,15 @@ __device__ __forceinline__ float screen_gap(const PairConst& P, float z0, float 
     const float ta0 = fabsf(ua0) - fmaf(hx, C, fmaf(hy, S, P.a0));
     const float ta1 = fabsf(ua1) - fmaf(hx, S, fmaf(hy, C, P.a1));
     return fmaxf(fmaxf(tb0, tb1), fmaxf(ta0, ta1));
+}
+
+template <int NDOF>
+__device__ __forceinline__ float screen_gap(const PairConst& P, float z0, float z1, float z2, float z3, float z4,
+                                            float& hmin)
+{
+    float s, c;
+    screen_trig(P.nst, P.th, z2, s, c);
+    return screen_gap_sc<NDOF>(P, z0, z1, s, c, z3, z4, hmin);
 }
 
 // true iff the sign of m is provably the exact decision (false for NaN anywhere)

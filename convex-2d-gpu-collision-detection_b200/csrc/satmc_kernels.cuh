@@ -577,28 +577,105 @@ __device__ __noinline__ unsigned sweep_sample_slow(const SweepShared& S, int c, 
     return hit;
 }
 
-// all 8 samples of super-group q (groups 2q, 2q+1) for setting c, normals regenerated: rare path of the main loop
-__device__ __noinline__ unsigned sweep_octet_slow(const SweepShared& S, int c, uint64_t q, uint32_t pid,
+// the 4 samples of group g for setting c, normals regenerated: rare path of the main loops
+__device__ __noinline__ unsigned sweep_group_slow(const SweepShared& S, int c, uint64_t g, uint32_t pid,
                                                   const PhiloxKeys& K, unsigned long long* exact_evals)
 {
+    float n[12];
+    group_normals<3>((uint32_t)g, (uint32_t)(g >> 32), pid, K, n);
     unsigned cnt = 0;
-    for (int h = 0; h < 2; h++) {
-        float n[12];
-        const uint64_t g = 2 * q + h;
-        group_normals<3>((uint32_t)g, (uint32_t)(g >> 32), pid, K, n);
-        for (int t = 0; t < 4; t++) cnt += sweep_sample_slow(S, c, n[3 * t], n[3 * t + 1], n[3 * t + 2], exact_evals);
-    }
+    for (int t = 0; t < 4; t++) cnt += sweep_sample_slow(S, c, n[3 * t], n[3 * t + 1], n[3 * t + 2], exact_evals);
     return cnt;
 }
 
-__global__ void __launch_bounds__(kThreads, 2) k_count_sweep(const satmc_pair* __restrict__ pairs, const float* __restrict__ sigmas,
-                                                             int n_cov, uint64_t hits_stride, const __grid_constant__ CountParams p)
+// all 8 samples of super-group q (groups 2q, 2q+1)
+__device__ __noinline__ unsigned sweep_octet_slow(const SweepShared& S, int c, uint64_t q, uint32_t pid,
+                                                  const PhiloxKeys& K, unsigned long long* exact_evals)
 {
-    __shared__ SweepShared s_sw[kWarps];
+    return sweep_group_slow(S, c, 2 * q, pid, K, exact_evals) + sweep_group_slow(S, c, 2 * q + 1, pid, K, exact_evals);
+}
+
+// Settings that share sd_theta share the relative angle of every sample, hence sin and cos: the sweep visits the
+// settings in order of sd_theta (S.order) and recomputes the two MUFUs only when it changes (a 4x4x4 grid: 4 times
+// per 64 settings).  One 4-sample group per lane and trip, so that the kept sines and cosines fit in registers.
+__device__ __forceinline__ void sweep_trip_shared_theta(SweepShared& S, const unsigned char* order, const PairConst& P,
+                                                        const CountParams& p, int n_cov, uint64_t q, bool mine, uint32_t pid,
+                                                        unsigned long long* ev, int lane)
+{
+    float n[24];
+    group_normals<3>((uint32_t)(2 * q), (uint32_t)((2 * q) >> 32), pid, p.keys, n);
+    group_normals<3>((uint32_t)(2 * q + 1), (uint32_t)((2 * q + 1) >> 32), pid, p.keys, n + 12);
+    float sn[8], cs[8];
+    uint32_t have = 0u, prev = 0u;
+    for (int r = 0; r < n_cov; r++) {
+        const int c = order[r];
+        const float4 k = S.k[c]; const float2 ee = S.e[c];
+        if (!have || __float_as_uint(ee.x) != prev) {                  // warp-uniform: r and the tables are
+            prev = __float_as_uint(ee.x); have = 1u;
+#pragma unroll
+            for (int t = 0; t < 8; t++) screen_trig(ee.x, P.th, n[3 * t + 2], sn[t], cs[t]);
+        }
+        PairConst Q = P;
+        Q.nkx0 = k.x; Q.nky0 = k.y; Q.kx1 = k.z; Q.nky1 = k.w; Q.nst = ee.x; Q.eps = ee.y;
+        unsigned cnt = 0;
+        bool decided = true;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            float hmin;
+            const float m = screen_gap_sc<3>(Q, n[3 * t], n[3 * t + 1], sn[t], cs[t], 0.f, 0.f, hmin);
+            cnt += __float_as_uint(m) >> 31;
+            decided = decided && screen_decided<3>(Q, m, hmin);
+        }
+        if (!decided && mine) cnt = sweep_octet_slow(S, c, q, pid, p.keys, ev);
+        cnt = __reduce_add_sync(0xffffffffu, mine ? cnt : 0u);
+        if (lane == 0) S.cnt[c] += cnt;
+    }
+}
+
+// Per launch: the order of the settings by sd_theta (rank sort on the bit patterns; any total order will do) and whether
+// sharing pays -- at least half of the settings can reuse their predecessor's sine and cosine.  Both k_count_sweep
+// variants are launched; the one the plan does not select returns at once.
+struct SweepPlan {
+    int share_theta;
+    unsigned char order[kSweepMax];
+};
+
+__global__ void k_sweep_plan(const float* __restrict__ sigmas, int n_cov, SweepPlan* plan)
+{
+    const int c = threadIdx.x;
+    int first = 0;
+    if (c < n_cov) {
+        const uint32_t key = __float_as_uint(__ldg(sigmas + 3 * c + 2));
+        int rank = 0; first = 1;
+        for (int j = 0; j < n_cov; j++) {
+            const uint32_t kj = __float_as_uint(__ldg(sigmas + 3 * j + 2));
+            rank += (kj < key) || (kj == key && j < c);
+            first &= !(kj == key && j < c);
+        }
+        plan->order[rank] = (unsigned char)c;
+    }
+    const int runs = __syncthreads_count(first);
+    if (c == 0) plan->share_theta = (2 * runs <= n_cov) ? 1 : 0;
+}
+
+// (measured for SHARE, which keeps 8 sines and 8 cosines besides the 24 normals: 8 warps per block at 128 registers with
+// 21 spill instructions in the setting loop 791 Gtests/s; 6 warps at 168 registers, nothing spilled, 753)
+__host__ __device__ constexpr int sweep_warps(bool) { return kWarps; }
+
+template <bool SHARE>
+__global__ void __launch_bounds__(32 * sweep_warps(SHARE), 2) k_count_sweep(const satmc_pair* __restrict__ pairs, const float* __restrict__ sigmas,
+                                                             int n_cov, uint64_t hits_stride, const __grid_constant__ CountParams p,
+                                                             const SweepPlan* __restrict__ plan)
+{
+    if ((plan->share_theta != 0) != SHARE) return;
+    constexpr int W = sweep_warps(SHARE);
+    __shared__ SweepShared s_sw[W];
+    __shared__ unsigned char s_order[kSweepMax];
+    if (SHARE) { if (threadIdx.x < kSweepMax) s_order[threadIdx.x] = plan->order[threadIdx.x]; __syncthreads(); }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     SweepShared& S = s_sw[warp];
-    const uint64_t stride = (uint64_t)gridDim.x * kWarps;
-    for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < p.n_items; item += stride) {
+    const uint64_t stride = (uint64_t)gridDim.x * W;
+    for (uint64_t item = (uint64_t)blockIdx.x * W + warp; item < p.n_items; item += stride) {
         const uint64_t pair = item / p.n_chunks;
         const uint32_t chunk_id = (uint32_t)(item - pair * p.n_chunks);
         float v[12];
@@ -627,7 +704,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_count_sweep(const satmc_pair* _
         const uint32_t pid = p.pair_id_offset + (uint32_t)pair;
         const uint64_t b = p.sample_offset + c_begin, e = b + c_len;
         const uint64_t q_lo = (b + 7) >> 3, q_hi = e >> 3;              // full 8-sample super-groups [q_lo, q_hi)
-        if (q_lo <= q_hi) {
+        if (SHARE && q_lo <= q_hi) {
+            for (uint64_t q0 = q_lo; q0 < q_hi; q0 += 32) {
+                const uint64_t q = q0 + (uint64_t)lane;
+                sweep_trip_shared_theta(S, s_order, P, p, n_cov, q, q < q_hi, pid, ev, lane);
+            }
+        } else if (q_lo <= q_hi) {
             for (uint64_t q0 = q_lo; q0 < q_hi; q0 += 32) {             // all 32 lanes stay in step; idle lanes count nothing
                 const uint64_t q = q0 + (uint64_t)lane;
                 const bool mine = q < q_hi;

@@ -468,13 +468,18 @@ def test_fused_vs_reference_kernel_statistically(ctx, dev, refgpu, workloads):
 
 
 # ---- covariance sweep with common random numbers -------------------------------------------------------------------
+@pytest.mark.parametrize("theta_levels", [0, 3])
 @pytest.mark.parametrize("n,offset", [(4096, 0), (1000, 0), (4099, 3), (7, 5), (20_001, 123_456_789_013)])
-def test_sweep_equals_fused_per_setting(ctx, dev, workloads, n, offset):
-    """satmc_count_fused_sweep[i, c] == satmc_count_fused(pair i with sigma c, same stream id), bit for bit."""
+def test_sweep_equals_fused_per_setting(ctx, dev, workloads, n, offset, theta_levels):
+    """satmc_count_fused_sweep[i, c] == satmc_count_fused(pair i with sigma c, same stream id), bit for bit.
+    theta_levels = 3: the settings take sd_theta from three values in shuffled order -- the kernel variant that visits the
+    settings sorted by sd_theta and keeps sine and cosine across equal values; 0: all different -- the plain variant."""
     pairs = workloads.dataset_pairs(23, seed=97)
     rng = np.random.default_rng(n)
     n_cov = {4096: 64, 1000: 100}.get(n, 37)                         # 100 settings = two kernel launches
     sig = np.sqrt(rng.uniform(0.0, 0.3, (n_cov, 3))).astype(np.float32)
+    if theta_levels:
+        sig[:, 2] = rng.choice(np.array([0.0, 0.21, 0.5], np.float32), n_cov)
     sig[0] = 0.0                                                     # a setting with no uncertainty at all
     d_pairs = dev.put(pairs); d_sig = dev.put(sig.ravel())
     for flags in (0, EXACT):
