@@ -468,7 +468,8 @@ k_count_streamed_tma(const __grid_constant__ DirectSrc src, const __grid_constan
     __syncwarp();
     uint32_t tiles_done = 0;                                          // running tile counter: stage and parity
     const uint64_t stride = (uint64_t)gridDim.x * kWarps;
-    for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < p.n_items; item += stride) {
+    for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < p.n_items;) {
+        const unsigned long long drawn = draw_ticket(p, lane);
         const uint64_t pair = item / p.n_chunks;
         const uint32_t chunk_id = (uint32_t)(item - pair * p.n_chunks);
         float v[12];
@@ -537,6 +538,7 @@ k_count_streamed_tma(const __grid_constant__ DirectSrc src, const __grid_constan
                 atomicAdd(p.hits + pair, (unsigned long long)cnt);
             }
         }
+        item = next_item(p, item, stride, drawn);
     }
 }
 
