@@ -770,6 +770,32 @@ __global__ void __launch_bounds__(32 * sweep_warps(SHARE), 2) k_count_sweep(cons
 // general convex polygons: same work decomposition, sampler and counting as k_count;
 // every sample is evaluated with the exact polygon SAT of satmc_poly.cuh (no screening pass yet)
 // ---------------------------------------------------------------------------------------------
+// samples of one work item; NR, NO as in poly_collide
+template <int NR, int NO, bool STREAMED>
+__device__ __forceinline__ unsigned poly_chunk(const PolyPairShared& S, const PolyRobotRegs& R, const CountParams& p, uint64_t pair,
+                                               uint64_t c_begin, uint64_t c_len, int lane)
+{
+    unsigned cnt = 0;
+    if (STREAMED) {
+        const float* z = p.z + pair * p.z_pair_stride + c_begin;
+        for (uint64_t i = (uint64_t)lane; i < c_len; i += 32)
+            cnt += poly_collide<NR, NO>(S, R, __ldg(z + i), __ldg(z + p.ldz + i), __ldg(z + 2 * p.ldz + i));
+    } else {
+        const uint32_t pid = p.pair_id_offset + (uint32_t)pair;
+        const uint64_t b = p.sample_offset + c_begin, e = b + c_len;
+        for (uint64_t g = (b >> 2) + (uint64_t)lane; 4 * g < e; g += 32) {    // 4-sample groups, ragged ends masked
+            float n[12];
+            group_normals<3>((uint32_t)g, (uint32_t)(g >> 32), pid, p.keys, n);
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const uint64_t sidx = 4 * g + t;
+                if (sidx >= b && sidx < e) cnt += poly_collide<NR, NO>(S, R, n[3 * t], n[3 * t + 1], n[3 * t + 2]);
+            }
+        }
+    }
+    return cnt;
+}
+
 template <bool STREAMED>
 __global__ void __launch_bounds__(kThreads, 2) k_count_poly(const float* __restrict__ pairs, const __grid_constant__ CountParams p)
 {
@@ -789,24 +815,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_count_poly(const float* __restr
         poly_load_robot(S, R);
         const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
         const uint64_t c_len = (c_begin + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - c_begin);
-        unsigned cnt = 0;
-        if (STREAMED) {
-            const float* z = p.z + pair * p.z_pair_stride + c_begin;
-            for (uint64_t i = (uint64_t)lane; i < c_len; i += 32)
-                cnt += poly_collide(S, R, __ldg(z + i), __ldg(z + p.ldz + i), __ldg(z + 2 * p.ldz + i));
-        } else {
-            const uint32_t pid = p.pair_id_offset + (uint32_t)pair;
-            const uint64_t b = p.sample_offset + c_begin, e = b + c_len;
-            for (uint64_t g = (b >> 2) + (uint64_t)lane; 4 * g < e; g += 32) {    // 4-sample groups, ragged ends masked
-                float n[12];
-                group_normals<3>((uint32_t)g, (uint32_t)(g >> 32), pid, p.keys, n);
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const uint64_t sidx = 4 * g + t;
-                    if (sidx >= b && sidx < e) cnt += poly_collide(S, R, n[3 * t], n[3 * t + 1], n[3 * t + 2]);
-                }
-            }
-        }
+        unsigned cnt;                                                  // straight-line code for the common equal vertex counts
+        const int shape = (S.nr == S.no) ? S.nr : 0;
+        if (shape == 4) cnt = poly_chunk<4, 4, STREAMED>(S, R, p, pair, c_begin, c_len, lane);
+        else if (shape == 3) cnt = poly_chunk<3, 3, STREAMED>(S, R, p, pair, c_begin, c_len, lane);
+        else if (shape == 6) cnt = poly_chunk<6, 6, STREAMED>(S, R, p, pair, c_begin, c_len, lane);
+        else if (shape == 8) cnt = poly_chunk<8, 8, STREAMED>(S, R, p, pair, c_begin, c_len, lane);
+        else cnt = poly_chunk<0, 0, STREAMED>(S, R, p, pair, c_begin, c_len, lane);
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (p.block_uniform) {
             if (lane == 0) s_part[warp] = cnt;

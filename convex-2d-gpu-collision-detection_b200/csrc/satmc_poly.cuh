@@ -66,11 +66,13 @@ __device__ __forceinline__ void poly_load_robot(const PolyPairShared& S, PolyRob
     for (int k = 0; k < kPolyMax; k++) { R.x[k] = (k < S.nr) ? S.rob_x[k] : 0.f; R.y[k] = (k < S.nr) ? S.rob_y[k] : 0.f; }
 }
 
-// decision for one sample: 1 = overlap.  nr, no are warp-uniform, so the `break`s below are uniform branches and a
-// quad-quad pair does half the work of an octagon-octagon pair.
+// decision for one sample: 1 = overlap.  NR, NO > 0: vertex counts known at compile time (straight-line code; the kernel
+// uses <4, 4> for quadrilaterals).  NR = NO = 0: counts read from S; they are warp-uniform, so the `break`s below are
+// uniform branches and a quad-quad pair does half the work of an octagon-octagon pair.
+template <int NR, int NO>
 __device__ __forceinline__ unsigned poly_collide(const PolyPairShared& S, const PolyRobotRegs& R, float z0, float z1, float z2)
 {
-    const int nr = S.nr, no = S.no;
+    const int nr = NR ? NR : S.nr, no = NO ? NO : S.no;
     const float dt = __fmul_rn(z2, S.sd_t);
     const float c = cosf(dt), s = sinf(dt);
     float ox[kPolyMax], oy[kPolyMax];

@@ -43,6 +43,9 @@ def test_polygon_decisions_match_oracle_bit_for_bit(ctx, dev, oracle, satmc):
         kr, ko = rng.integers(3, 9), rng.integers(3, 9)
         robots.append(random_convex(rng, kr, rng.uniform(0.5, 2.5)))
         obstacles.append(random_convex(rng, ko, rng.uniform(0.3, 2.5)))
+    for k in (3, 4, 6, 8, 4, 8):                                                   # equal counts: the straight-line variants
+        robots.append(random_convex(rng, k, rng.uniform(0.5, 2.5)))
+        obstacles.append(random_convex(rng, k, rng.uniform(0.3, 2.5)))
     robots += [regular(1, 0.0), regular(2, 1.0), rect_poly(4.07, 1.74)]          # point, segment, the reference robot
     obstacles += [regular(5, 1.0), regular(8, 1.5), regular(1, 0.0)]
     n = len(robots)
