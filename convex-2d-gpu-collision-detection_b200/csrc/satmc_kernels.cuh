@@ -770,29 +770,82 @@ __global__ void __launch_bounds__(32 * sweep_warps(SHARE), 2) k_count_sweep(cons
 // general convex polygons: same work decomposition, sampler and counting as k_count;
 // every sample is evaluated with the exact polygon SAT of satmc_poly.cuh (no screening pass yet)
 // ---------------------------------------------------------------------------------------------
-// samples of one work item; NR, NO as in poly_collide
-template <int NR, int NO, bool STREAMED>
-__device__ __forceinline__ unsigned poly_chunk(const PolyPairShared& S, const PolyRobotRegs& R, const CountParams& p, uint64_t pair,
-                                               uint64_t c_begin, uint64_t c_len, int lane)
+// Undecided samples of a warp, waiting for the exact pass: the screening pass decides most samples, and running the
+// exact SAT for the rest lane by lane would leave the warp mostly idle.  Samples are appended with a ballot (warp-
+// uniform fill count) and evaluated 32 at a time with all lanes busy -- by ONE copy of the exact code per vertex-count
+// variant (poly_queue_drain), called once per trip of the sample loop.
+constexpr unsigned kPolyQueueCap = 160;                               // 31 left over + 4 x 32 appended per trip
+struct PolyQueue { float z[3][kPolyQueueCap]; };
+
+// evaluates queued samples from the top of the queue, 32 at a time; with `all` also the last, partly filled pass
+template <int NR, int NO>
+__device__ __forceinline__ unsigned poly_queue_drain(const PolyPairShared& S, const PolyRobotRegs& R, PolyQueue& Q, unsigned& fill,
+                                                     bool all, int lane, unsigned long long* exact_evals)
 {
-    unsigned cnt = 0;
+    unsigned hit = 0;
+    __syncwarp();
+    while (fill >= 32u || (all && fill > 0u)) {
+        const unsigned n = fill < 32u ? fill : 32u;
+        fill -= n;
+        if ((unsigned)lane < n) hit += poly_collide<NR, NO>(S, R, Q.z[0][fill + lane], Q.z[1][fill + lane], Q.z[2][fill + lane]);
+        if (exact_evals && lane == 0) atomicAdd(exact_evals, (unsigned long long)n);
+    }
+    __syncwarp();
+    return hit;
+}
+
+// one sample through the screening pass; undecided ones are queued.  `fill` is warp-uniform.
+template <int NR>
+__device__ __forceinline__ unsigned poly_sample(const PolyPairShared& S, const PolyScreenRegs<NR>& C, PolyQueue& Q, unsigned& fill,
+                                                bool valid, bool screen, float z0, float z1, float z2, int lane)
+{
+    const int r = (valid && screen) ? poly_screen<NR>(S, C, z0, z1, z2) : 0;
+    const bool und = valid && r == 0;
+    const unsigned mask = __ballot_sync(0xffffffffu, und);
+    if (und) {
+        const unsigned pos = fill + __popc(mask & ((1u << lane) - 1u));
+        Q.z[0][pos] = z0; Q.z[1][pos] = z1; Q.z[2][pos] = z2;
+    }
+    fill += __popc(mask);
+    return (r == 2) ? 1u : 0u;
+}
+
+// samples of one work item; NR, NO as in poly_collide.  All 32 lanes walk the loops in step (ballots inside).
+template <int NR, int NO, bool STREAMED>
+__device__ __forceinline__ unsigned poly_chunk(const PolyPairShared& S, const PolyRobotRegs& R, PolyQueue& Q, const CountParams& p,
+                                               uint64_t pair, uint64_t c_begin, uint64_t c_len, int lane)
+{
+    unsigned cnt = 0, fill = 0;
+    PolyScreenRegs<NR> C;
+    poly_load_screen<NR>(S, C);
+    const bool screen = !(p.flags & SATMC_EXACT_ONLY);
+    unsigned long long* ev = screen ? p.exact_evals : nullptr;
     if (STREAMED) {
         const float* z = p.z + pair * p.z_pair_stride + c_begin;
-        for (uint64_t i = (uint64_t)lane; i < c_len; i += 32)
-            cnt += poly_collide<NR, NO>(S, R, __ldg(z + i), __ldg(z + p.ldz + i), __ldg(z + 2 * p.ldz + i));
+        for (uint64_t i0 = 0; i0 < c_len; i0 += 32) {
+            const uint64_t i = i0 + (uint64_t)lane;
+            const bool valid = i < c_len;
+            const float z0 = valid ? __ldg(z + i) : 0.f, z1 = valid ? __ldg(z + p.ldz + i) : 0.f, z2 = valid ? __ldg(z + 2 * p.ldz + i) : 0.f;
+            cnt += poly_sample<NR>(S, C, Q, fill, valid, screen, z0, z1, z2, lane);
+            if (fill >= 32u) cnt += poly_queue_drain<NR, NO>(S, R, Q, fill, false, lane, ev);
+        }
     } else {
         const uint32_t pid = p.pair_id_offset + (uint32_t)pair;
         const uint64_t b = p.sample_offset + c_begin, e = b + c_len;
-        for (uint64_t g = (b >> 2) + (uint64_t)lane; 4 * g < e; g += 32) {    // 4-sample groups, ragged ends masked
+        const uint64_t g_end = (e + 3) >> 2;
+        for (uint64_t g0 = b >> 2; g0 < g_end; g0 += 32) {               // 4-sample groups, ragged ends masked
+            const uint64_t g = g0 + (uint64_t)lane;
             float n[12];
             group_normals<3>((uint32_t)g, (uint32_t)(g >> 32), pid, p.keys, n);
 #pragma unroll
             for (int t = 0; t < 4; t++) {
                 const uint64_t sidx = 4 * g + t;
-                if (sidx >= b && sidx < e) cnt += poly_collide<NR, NO>(S, R, n[3 * t], n[3 * t + 1], n[3 * t + 2]);
+                cnt += poly_sample<NR>(S, C, Q, fill, sidx >= b && sidx < e, screen, n[3 * t], n[3 * t + 1], n[3 * t + 2], lane);
             }
+            if (fill >= 32u) cnt += poly_queue_drain<NR, NO>(S, R, Q, fill, false, lane, ev);
         }
     }
+    cnt += poly_queue_drain<NR, NO>(S, R, Q, fill, true, lane, ev);
     return cnt;
 }
 
@@ -800,6 +853,7 @@ template <bool STREAMED>
 __global__ void __launch_bounds__(kThreads, 2) k_count_poly(const float* __restrict__ pairs, const __grid_constant__ CountParams p)
 {
     __shared__ PolyPairShared s_poly[kWarps];
+    __shared__ PolyQueue s_queue[kWarps];
     __shared__ unsigned s_part[kWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t stride = (uint64_t)gridDim.x * kWarps;
@@ -808,7 +862,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_count_poly(const float* __restr
         const uint64_t pair = item / p.n_chunks;
         const uint32_t chunk_id = (uint32_t)(item - pair * p.n_chunks);
         __syncwarp();
-        if (lane == 0) poly_prologue(s_poly[warp], pairs + pair * 40);          // 160-byte descriptors
+        if (lane == 0) {
+            poly_prologue(s_poly[warp], pairs + pair * 40);                        // 160-byte descriptors
+            poly_screen_prologue(s_poly[warp], !(p.flags & SATMC_EXACT_ONLY));
+        }
         __syncwarp();
         const PolyPairShared& S = s_poly[warp];
         PolyRobotRegs R;
@@ -817,11 +874,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_count_poly(const float* __restr
         const uint64_t c_len = (c_begin + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - c_begin);
         unsigned cnt;                                                  // straight-line code for the common equal vertex counts
         const int shape = (S.nr == S.no) ? S.nr : 0;
-        if (shape == 4) cnt = poly_chunk<4, 4, STREAMED>(S, R, p, pair, c_begin, c_len, lane);
-        else if (shape == 3) cnt = poly_chunk<3, 3, STREAMED>(S, R, p, pair, c_begin, c_len, lane);
-        else if (shape == 6) cnt = poly_chunk<6, 6, STREAMED>(S, R, p, pair, c_begin, c_len, lane);
-        else if (shape == 8) cnt = poly_chunk<8, 8, STREAMED>(S, R, p, pair, c_begin, c_len, lane);
-        else cnt = poly_chunk<0, 0, STREAMED>(S, R, p, pair, c_begin, c_len, lane);
+        if (shape == 4) cnt = poly_chunk<4, 4, STREAMED>(S, R, s_queue[warp], p, pair, c_begin, c_len, lane);
+        else if (shape == 3) cnt = poly_chunk<3, 3, STREAMED>(S, R, s_queue[warp], p, pair, c_begin, c_len, lane);
+        else if (shape == 6) cnt = poly_chunk<6, 6, STREAMED>(S, R, s_queue[warp], p, pair, c_begin, c_len, lane);
+        else if (shape == 8) cnt = poly_chunk<8, 8, STREAMED>(S, R, s_queue[warp], p, pair, c_begin, c_len, lane);
+        else cnt = poly_chunk<0, 0, STREAMED>(S, R, s_queue[warp], p, pair, c_begin, c_len, lane);
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (p.block_uniform) {
             if (lane == 0) s_part[warp] = cnt;

@@ -12,6 +12,7 @@
 // gives bit-identical decisions.  Vertices are counter-clockwise, 1..8 per polygon.
 #pragma once
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include <stdint.h>
 
 namespace satmc {
@@ -26,7 +27,111 @@ struct PolyPairShared {
     float obs_x[kPolyMax], obs_y[kPolyMax];      // obstacle vertices, nominal
     float sd_x, sd_y, sd_t;
     int nr, no;
+    // screening pass (see poly_screen): robot-normal thresholds against the obstacle's bounding circle, and the
+    // inscribed-circle test
+    float scr_hi[kPolyMax], scr_lo[kPolyMax];    // d_i > scr_hi[i] or d_i < scr_lo[i]  =>  separated on robot normal i
+    float crx, cry, t2;                          // |centre - (crx, cry)|^2 < t2  =>  the inscribed circles overlap deeply
 };
+
+// Inscribed radius about (cx, cy) of the vertex chain (x, y)[0..n): the smallest signed distance to an edge line, counter-
+// clockwise positive, clamped at 0.  A disc of that radius lies inside every edge half-plane, so the chain winds around
+// it and it lies in the convex hull of the vertices -- for any input, convex or not; 0 for clockwise or degenerate input.
+__device__ __forceinline__ float poly_inradius(const float* x, const float* y, int n, float cx, float cy)
+{
+    if (n < 3) return 0.f;
+    float r = CUDART_INF_F;
+    for (int i = 0; i < n; i++) {
+        const int j = (i + 1 == n) ? 0 : i + 1;
+        const float ex = x[j] - x[i], ey = y[j] - y[i];
+        const float el = sqrtf(fmaf(ex, ex, ey * ey));
+        const float d = ((x[i] - cx) * ey - (y[i] - cy) * ex) / el;
+        if (!(d > 0.f)) return 0.f;                                   // also NaN (zero-length edge)
+        r = fminf(r, d);
+    }
+    return r * 0.99999f;
+}
+
+// Screening constants (lane 0, after the exact constants).  With c = (z0 sd_x, z1 sd_y) the sampled position of the
+// obstacle's local origin, every sampled obstacle vertex lies within rho of c whatever the rotation, so on robot
+// normal n_i the obstacle projects inside [n_i.c - rho |n_i|, n_i.c + rho |n_i|]: if that interval clears the robot's
+// own extent [rmin_i, rmax_i] by more than the rounding of both evaluations, the exact pass finds axis i separating.
+// Conversely, if the circle of radius rin_o about c overlaps the robot's inscribed circle by more than that rounding,
+// the projections overlap on every axis and the exact pass reports a collision.  Rounding: every quantity involved is
+// a sum of at most four products of magnitudes <= M carrying at most six roundings of 2^-24 each (precise sinf/cosf:
+// 2 ulp), i.e. below 2^-20 M; the margins use eta = 2^-16 on the sum of the magnitudes, with |z0|, |z1| <= 8 (samples
+// beyond that are not screened).  Anything non-finite makes a comparison false, which means "not decided".
+__device__ __forceinline__ void poly_screen_prologue(PolyPairShared& S, bool enable)
+{
+    const float eta = 1.52587890625e-05f, up = 1.000002f;
+    const int nr = S.nr, no = S.no;
+    float rho = 0.f;
+    for (int k = 0; k < no; k++) rho = fmaxf(rho, sqrtf(fmaf(S.obs_x[k], S.obs_x[k], S.obs_y[k] * S.obs_y[k])));
+    rho *= up;
+    const float X = 8.0f * fabsf(S.sd_x), Y = 8.0f * fabsf(S.sd_y);
+    for (int i = 0; i < nr; i++) {
+        const float nx = S.rnx[i], ny = S.rny[i];
+        const float ext = rho * (sqrtf(fmaf(nx, nx, ny * ny)) * up);
+        const float m = eta * (fabsf(nx) * X + fabsf(ny) * Y + ext + fmaxf(fabsf(S.rmin[i]), fabsf(S.rmax[i])));
+        float hi = S.rmax[i] + ext + m, lo = S.rmin[i] - ext - m;
+        hi += fabsf(hi) * 2e-6f; lo -= fabsf(lo) * 2e-6f;
+        S.scr_hi[i] = enable ? hi : CUDART_INF_F;
+        S.scr_lo[i] = enable ? lo : -CUDART_INF_F;
+    }
+    float cx = 0.f, cy = 0.f;
+    for (int k = 0; k < nr; k++) { cx += S.rob_x[k]; cy += S.rob_y[k]; }
+    cx /= (float)nr; cy /= (float)nr;
+    float rho_r = 0.f;
+    for (int k = 0; k < nr; k++) rho_r = fmaxf(rho_r, sqrtf(fmaf(S.rob_x[k] - cx, S.rob_x[k] - cx, (S.rob_y[k] - cy) * (S.rob_y[k] - cy))));
+    // both centres must lie strictly inside their polygon (inradius 0 = centre outside, on the boundary, or degenerate)
+    const float rin_r = poly_inradius(S.rob_x, S.rob_y, nr, cx, cy), rin_o = poly_inradius(S.obs_x, S.obs_y, no, 0.f, 0.f);
+    const float t = rin_r + rin_o - eta * (fabsf(cx) + fabsf(cy) + X + Y + rho + rho_r);
+    S.crx = cx; S.cry = cy;
+    S.t2 = (enable && rin_r > 0.f && rin_o > 0.f && t > 0.f) ? t * t * 0.99999f : -1.0f;
+}
+
+// The screening constants of the current pair in registers (NR > 0) or left in shared memory (NR = 0: general loop).
+template <int NR>
+struct PolyScreenRegs {
+    float nx[NR ? NR : 1], ny[NR ? NR : 1], hi[NR ? NR : 1], lo[NR ? NR : 1];
+    float sd_x, sd_y, sd_t, crx, cry, t2;
+};
+
+template <int NR>
+__device__ __forceinline__ void poly_load_screen(const PolyPairShared& S, PolyScreenRegs<NR>& C)
+{
+#pragma unroll
+    for (int i = 0; i < NR; i++) { C.nx[i] = S.rnx[i]; C.ny[i] = S.rny[i]; C.hi[i] = S.scr_hi[i]; C.lo[i] = S.scr_lo[i]; }
+    C.sd_x = S.sd_x; C.sd_y = S.sd_y; C.sd_t = S.sd_t; C.crx = S.crx; C.cry = S.cry; C.t2 = S.t2;
+}
+
+// Screening of one sample: 0 = not decided (run the exact pass), 1 = separated, 2 = overlapping.  NR as in poly_collide.
+template <int NR>
+__device__ __forceinline__ int poly_screen(const PolyPairShared& S, const PolyScreenRegs<NR>& C, float z0, float z1, float z2)
+{
+    const float cx = z0 * C.sd_x, cy = z1 * C.sd_y;
+    bool sep = false;
+    if (NR) {
+#pragma unroll
+        for (int i = 0; i < NR; i++) {
+            const float d = fmaf(C.nx[i], cx, C.ny[i] * cy);
+            sep = sep || (d > C.hi[i]) || (d < C.lo[i]);
+        }
+    } else {
+        const int nr = S.nr;
+#pragma unroll
+        for (int i = 0; i < kPolyMax; i++) {
+            if (i >= nr) break;
+            const float d = fmaf(S.rnx[i], cx, S.rny[i] * cy);
+            sep = sep || (d > S.scr_hi[i]) || (d < S.scr_lo[i]);
+        }
+    }
+    const float dx = cx - C.crx, dy = cy - C.cry;
+    const bool col = fmaf(dx, dx, dy * dy) < C.t2;
+    // the rotation angle itself does not matter (bounding / inscribed circles), but a non-finite one makes every exact
+    // projection NaN, which the exact pass counts as a collision like the reference does: not screened
+    const bool in_range = (fabsf(z0) <= 8.0f) && (fabsf(z1) <= 8.0f) && (fabsf(z2 * C.sd_t) <= 3.0e38f);
+    return in_range ? (sep ? 1 : (col ? 2 : 0)) : 0;
+}
 
 // lane 0 of the warp fills the shared block from the descriptor (160 bytes: see satmc_poly_pair in satmc.h)
 __device__ __forceinline__ void poly_prologue(PolyPairShared& S, const float* __restrict__ d)

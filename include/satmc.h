@@ -167,7 +167,8 @@ typedef struct satmc_poly_pair {
     float obstacle[2 * SATMC_POLY_MAX];/* obstacle vertices in its nominal frame                           */
 } satmc_poly_pair;
 
-/* Same semantics as satmc_count_fused / satmc_count_streamed (3 normals per sample: x, y, theta). */
+/* Same semantics as satmc_count_fused / satmc_count_streamed (3 normals per sample: x, y, theta).
+ * SATMC_EXACT_ONLY bypasses the polygon screening pass (every sample through the exact SAT); counts are identical. */
 int satmc_count_fused_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs, uint64_t n_pairs,
                                uint64_t n_samples, uint64_t seed, uint64_t sample_offset,
                                uint32_t pair_id_offset, uint64_t* d_hits, uint32_t flags);

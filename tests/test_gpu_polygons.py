@@ -114,3 +114,55 @@ def test_polygon_fused_sharding_and_float64_probability(ctx, dev, satmc):
         pm = (p + p_ref) / 2
         assert abs(p - p_ref) < 4.9 * math.sqrt(pm * (1 - pm) * (1 / n + 1 / m)) + 1e-9, (i, p, p_ref)
     assert 0.01 < (whole / n).min() and (whole / n).max() < 0.99
+
+
+def test_polygon_screening_equals_exact(ctx, dev, workloads, satmc):
+    """The polygon screening pass (robot normals against the obstacle's bounding circle; inscribed circles) may only decide
+    what the exact SAT would decide the same way.  Differential test, counts with screening == counts with every sample
+    through the exact pass (SATMC_EXACT_ONLY), over: rectangles of the dataset prior, random convex polygons of mixed
+    vertex counts placed around first contact, the same polygons given CLOCKWISE, non-convex stars, shapes whose local
+    origin lies outside (inradius 0), points and segments; fused and streamed entry points."""
+    rng = np.random.default_rng(31)
+    EXACT = 0x2
+
+    def both(pp, n, seed):
+        ctx.exact_evals(reset=True)
+        fast = poly_count(ctx, dev, pp, n=n, seed=seed)
+        evals = ctx.exact_evals(reset=True)
+        exact = poly_count(ctx, dev, pp, n=n, seed=seed, flags=EXACT)
+        np.testing.assert_array_equal(fast, exact)
+        return fast, evals
+
+    # rectangles of the dataset prior: most samples must be decided by the screening pass
+    pairs = workloads.dataset_pairs(20_000, seed=71)
+    pp = satmc.make_poly_pairs([rect_poly(p["rw"], p["rh"]) for p in pairs], [rect_poly(p["ow"], p["oh"]) for p in pairs],
+                               pairs["rx"], pairs["ry"], pairs["rtheta"], pairs["sd_x"], pairs["sd_y"], pairs["sd_theta"])
+    fast, evals = both(pp, 4_000, 5)
+    assert 0 < fast.sum() and evals < 0.4 * pairs.size * 4_000
+
+    # mixed shapes around first contact
+    robots, obstacles = [], []
+    for i in range(3_000):
+        kr, ko = rng.integers(1, 9), rng.integers(1, 9)
+        a = random_convex(rng, max(kr, 3), rng.uniform(0.3, 2.5))[:kr]
+        b = random_convex(rng, max(ko, 3), rng.uniform(0.2, 2.5))[:ko]
+        shift = rng.uniform(-1.5, 1.5, 2).astype(np.float32) if i % 3 == 0 else np.zeros(2, np.float32)   # local origin off-centre / outside
+        kind = i % 5
+        if kind == 1:
+            a, b = a[::-1].copy(), b[::-1].copy()                                                      # clockwise input
+        if kind == 2 and ko >= 5:
+            b = (b * np.where(np.arange(ko) % 2 == 0, 1.0, 0.35)[:, None]).astype(np.float32)           # non-convex star
+        robots.append(a); obstacles.append((b + shift).astype(np.float32))
+    n = len(robots)
+    d = rng.uniform(0.0, 5.0, n); ang = rng.uniform(0, 2 * np.pi, n)
+    sig = 10.0 ** rng.uniform(-3, -0.2, (3, n))
+    pp = satmc.make_poly_pairs(robots, obstacles, d * np.cos(ang), d * np.sin(ang), rng.uniform(0, 6.28, n), sig[0], sig[1], sig[2])
+    fast, evals = both(pp, 6_000, 6)
+    frac = fast / 6_000
+    assert (frac == 0).any() and (frac == 1).any() and ((frac > 0.05) & (frac < 0.95)).sum() > 100
+    assert evals < n * 6_000                                        # and the screening pass did decide something
+
+    # streamed entry point, ragged size, hostile normals
+    z = rng.standard_normal((3, 3_001)).astype(np.float32)
+    z[:, 7] = [np.nan, 0, 0]; z[:, 8] = [0, np.inf, 0]; z[:, 9] = [9.0, -9.0, 1e30]; z[:, 10] = [0, 0, np.nan]
+    np.testing.assert_array_equal(poly_count(ctx, dev, pp[:500], z=z), poly_count(ctx, dev, pp[:500], z=z, flags=EXACT))
