@@ -388,6 +388,23 @@ def extras(ctx, mod, wl, torch, hbm_peak, src):
     one = put(wl.cfg2_pair()); d_h1 = torch.zeros(1, dtype=torch.int64, device="cuda")
     ms = timed(lambda: ctx.count_fused(one, 1, 1_000_000, 7, d_h1), reps=20, warm=5)
     out["cfg2_fused_1pair_1e6"] = {"tests_per_s": 1e6 / ms * 1e3, "ms": ms}
+    # general convex polygons: the cfg 3 rectangles given as 4-vertex polygons, and octagons of similar size
+    pr = wl.dataset_pairs(100_000, 3)
+    d_hp = torch.zeros(pr.size, dtype=torch.int64, device="cuda")
+
+    def rect_verts(w, h):
+        return np.stack([-w / 2, -h / 2, w / 2, -h / 2, w / 2, h / 2, -w / 2, h / 2], 1).reshape(-1, 4, 2).astype(np.float32)
+
+    def octagons(w, h):
+        a = 2 * np.pi * np.arange(8) / 8
+        return np.stack([0.5 * w[:, None] * np.cos(a), 0.5 * h[:, None] * np.sin(a)], 2).astype(np.float32)
+    for name, rv, ov in (("polygons_4x4_cfg3_rectangles", rect_verts(pr["rw"], pr["rh"]), rect_verts(pr["ow"], pr["oh"])),
+                         ("polygons_8x8_octagons", octagons(pr["rw"], pr["rh"]), octagons(pr["ow"], pr["oh"]))):
+        ppoly = mod.make_poly_pairs(list(rv), list(ov), pr["rx"], pr["ry"], pr["rtheta"], pr["sd_x"], pr["sd_y"], pr["sd_theta"])
+        d_poly = torch.from_numpy(np.ascontiguousarray(ppoly).view(np.uint8).view(np.float32)).cuda()
+        ms = timed(lambda: ctx.count_fused_polygons(d_poly, ppoly.size, 10_000, 7, d_hp), reps=3)
+        out[name] = {"tests_per_s": ppoly.size * 1e4 / ms * 1e3, "ms": ms, "mean_p": float(d_hp.sum().item()) / (ppoly.size * 1e4),
+                     "what": "satmc_count_fused_polygons: circle-based screening pass, undecided samples compacted per warp, exact polygon SAT"}
     # the adaptive z-test batch (what generate_dataset / compute_collision_probability do per file)
     pairs = wl.dataset_pairs(100_000, 3)
     rb, poses, sds, pi, si, pos = wl.reference_tables(pairs)
