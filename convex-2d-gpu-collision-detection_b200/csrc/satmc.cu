@@ -281,6 +281,10 @@ static int plan_items(satmc_ctx* ctx, CountParams& p, int bps, uint64_t& blocks,
 static void use_tickets(satmc_ctx* ctx, CountParams& p, uint64_t blocks)
 {
     if (p.block_uniform || p.n_items <= blocks * (uint64_t)kWarps) return;
+    // ticket_base is a launch parameter: a captured launch replayed from a CUDA graph would see a stale one.  While the
+    // stream is capturing, keep the static order (same counts, a few per cent slower).
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ctx->stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { cudaGetLastError(); return; }
     p.ticket = ctx->d_ticket + ctx->ticket_sel;
     p.ticket_base = ctx->ticket_next[ctx->ticket_sel];
     ctx->ticket_next[ctx->ticket_sel] += p.n_items;

@@ -425,6 +425,33 @@ def test_deferred_cold_groups_long_items(ctx, dev, oracle, satmc, workloads):
     np.testing.assert_array_equal(part, oracle.count_fused_batch(pairs[:2], 2_000, 77, sample_offset=lo))
 
 
+def test_launches_can_be_captured_in_a_cuda_graph(dev, satmc, workloads):
+    """A captured satmc_count_fused must give the same counts on every replay (the dynamic work distribution keeps host-side
+    state per launch, so captured launches fall back to the static order)."""
+    import torch
+    pairs = workloads.dataset_pairs(30_000, seed=811)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        c2 = satmc.Context(0, s.cuda_stream)
+        d_pairs = dev.put(pairs); d_hits = dev.zeros(pairs.size, np.uint64)
+        c2.count_fused(d_pairs, pairs.size, 700, 5, d_hits)              # direct launch: dynamic order
+        c2.synchronize()
+        want = dev.get(d_hits, np.uint64).copy()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            c2.count_fused(d_pairs, pairs.size, 700, 5, d_hits)
+        for _ in range(3):
+            d_hits.zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(dev.get(d_hits, np.uint64), want)
+        c2.count_fused(d_pairs, pairs.size, 700, 5, d_hits)              # and direct launches still work afterwards
+        c2.synchronize()
+        np.testing.assert_array_equal(dev.get(d_hits, np.uint64), want)
+        c2.close()
+    assert want.sum() > 0
+
+
 def test_fused_agrees_with_cpu_restatement_statistically(ctx, dev, oracle, workloads):
     """GPU sampler (MUFU) vs the oracle's libm restatement of the same sampler: normals agree to ~1e-6, so the
     counts differ only where a sample sits within ~1e-6 of the decision boundary: <= 3 per 1e5 samples."""
