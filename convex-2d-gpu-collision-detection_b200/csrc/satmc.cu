@@ -475,7 +475,7 @@ int satmc_count_fused_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs, u
     DeviceGuard g(ctx->device);
     CountParams p{};
     p.n_pairs = n_pairs; p.n_samples = n_samples; p.sample_offset = sample_offset; p.pair_id_offset = pair_id_offset;
-    philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), p.keys); p.flags = flags & (SATMC_ACCUMULATE | SATMC_EXACT_ONLY);
+    philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), p.keys); p.flags = flags & (SATMC_ACCUMULATE | SATMC_EXACT_ONLY); p.exact_evals = ctx->d_exact_evals;
     p.hits = reinterpret_cast<unsigned long long*>(d_hits);
     if (n_pairs == 0 || n_samples == 0) {
         if (n_pairs && !(flags & SATMC_ACCUMULATE)) CU(ctx, cudaMemsetAsync(d_hits, 0, n_pairs * sizeof(uint64_t), ctx->stream));
@@ -502,7 +502,7 @@ int satmc_count_streamed_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs
     if (rc) return rc;
     DeviceGuard g(ctx->device);
     CountParams p{};
-    p.n_pairs = n_pairs; p.n_samples = n_samples; p.flags = flags & (SATMC_ACCUMULATE | SATMC_EXACT_ONLY);
+    p.n_pairs = n_pairs; p.n_samples = n_samples; p.flags = flags & (SATMC_ACCUMULATE | SATMC_EXACT_ONLY); p.exact_evals = ctx->d_exact_evals;
     p.hits = reinterpret_cast<unsigned long long*>(d_hits);
     p.z = d_z; p.ldz = ldz; p.z_pair_stride = z_pair_stride; p.ndof = 3;
     if (n_pairs == 0 || n_samples == 0) {

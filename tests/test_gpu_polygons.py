@@ -138,7 +138,7 @@ def test_polygon_screening_equals_exact(ctx, dev, workloads, satmc):
     pp = satmc.make_poly_pairs([rect_poly(p["rw"], p["rh"]) for p in pairs], [rect_poly(p["ow"], p["oh"]) for p in pairs],
                                pairs["rx"], pairs["ry"], pairs["rtheta"], pairs["sd_x"], pairs["sd_y"], pairs["sd_theta"])
     fast, evals = both(pp, 4_000, 5)
-    assert 0 < fast.sum() and evals < 0.4 * pairs.size * 4_000
+    assert 0 < fast.sum() and 0 < evals < 0.4 * pairs.size * 4_000
 
     # mixed shapes around first contact
     robots, obstacles = [], []
@@ -160,9 +160,45 @@ def test_polygon_screening_equals_exact(ctx, dev, workloads, satmc):
     fast, evals = both(pp, 6_000, 6)
     frac = fast / 6_000
     assert (frac == 0).any() and (frac == 1).any() and ((frac > 0.05) & (frac < 0.95)).sum() > 100
-    assert evals < n * 6_000                                        # and the screening pass did decide something
+    assert 0 < evals < n * 6_000                                    # and the screening pass did decide something
 
     # streamed entry point, ragged size, hostile normals
     z = rng.standard_normal((3, 3_001)).astype(np.float32)
     z[:, 7] = [np.nan, 0, 0]; z[:, 8] = [0, np.inf, 0]; z[:, 9] = [9.0, -9.0, 1e30]; z[:, 10] = [0, 0, np.nan]
     np.testing.assert_array_equal(poly_count(ctx, dev, pp[:500], z=z), poly_count(ctx, dev, pp[:500], z=z, flags=EXACT))
+
+
+def test_polygon_screening_margin_at_its_own_boundary(ctx, dev, satmc):
+    """Worst case for the separating test of the screening pass: the obstacle's bounding circle tangent to a robot edge
+    line, free rotation (so that some samples point a vertex straight at the edge and the true gap is only the margin),
+    position noise of the order of the margin (so that samples fall on both sides of the screening threshold).  Where
+    the screening pass says "separated" the exact pass must find a separating axis: counts with == counts without."""
+    rng = np.random.default_rng(41)
+    EXACT = 0x2
+    robots, obstacles, px, py, th, sig = [], [], [], [], [], []
+    for i in range(3_000):
+        kr, ko = rng.integers(3, 9), rng.integers(3, 9)
+        a = random_convex(rng, kr, rng.uniform(0.3, 2.5)).astype(np.float64)
+        b = random_convex(rng, ko, rng.uniform(0.2, 2.5)).astype(np.float64)
+        if i % 2:
+            b = b + rng.uniform(-0.8, 0.8, 2)                                    # bounding circle not centred on the shape
+        t = rng.uniform(0, 2 * np.pi); c, s = np.cos(t), np.sin(t)
+        aw = np.stack([c * a[:, 0] - s * a[:, 1], s * a[:, 0] + c * a[:, 1]], 1)    # rotated robot, before translation
+        e = rng.integers(0, kr); j = (e + 1) % kr
+        ed = aw[j] - aw[e]; u = np.array([ed[1], -ed[0]]); u /= np.hypot(*u)       # outward unit normal of edge e
+        rho = np.hypot(b[:, 0], b[:, 1]).max()
+        lam = rng.uniform(0.2, 0.8)
+        foot = aw[e] + lam * ed                                                   # point of the edge nearest to the circle centre
+        p = -(foot + rho * u)                                                     # puts the edge line at distance rho from the origin
+        robots.append(a.astype(np.float32)); obstacles.append(b.astype(np.float32))
+        px.append(p[0]); py.append(p[1]); th.append(t)
+        sig.append(3e-5 * (rho + np.abs(p).max()) * 10.0 ** rng.uniform(-1, 1))
+    sig = np.array(sig)
+    pp = satmc.make_poly_pairs(robots, obstacles, px, py, th, sig, sig, 3.0)
+    n = 20_000
+    ctx.exact_evals(reset=True)
+    fast = poly_count(ctx, dev, pp, n=n, seed=3)
+    evals = ctx.exact_evals(reset=True)
+    exact = poly_count(ctx, dev, pp, n=n, seed=3, flags=EXACT)
+    np.testing.assert_array_equal(fast, exact)
+    assert 0.02 * pp.size * n < evals < 0.98 * pp.size * n             # samples on both sides of the screening threshold
