@@ -202,3 +202,32 @@ def test_polygon_screening_margin_at_its_own_boundary(ctx, dev, satmc):
     exact = poly_count(ctx, dev, pp, n=n, seed=3, flags=EXACT)
     np.testing.assert_array_equal(fast, exact)
     assert 0.02 * pp.size * n < evals < 0.98 * pp.size * n             # samples on both sides of the screening threshold
+
+
+def test_polygon_screening_margin_inscribed_circles(ctx, dev, satmc):
+    """Worst case for the "overlapping" test of the screening pass: two regular polygons facing each other edge to
+    edge, no rotation, inscribed circles tangent, position noise of the order of the margin: where the screening pass
+    says "overlapping" the true overlap is only the margin deep, and the exact pass must still find no separating axis."""
+    rng = np.random.default_rng(43)
+    EXACT = 0x2
+    robots, obstacles, px, py, sig = [], [], [], [], []
+    for i in range(2_000):
+        kr, ko = rng.choice([3, 4, 5, 6, 8], 2)
+        Rr, Ro = rng.uniform(0.3, 2.5), rng.uniform(0.2, 2.5)
+        ph = rng.uniform(0, 2 * np.pi)
+        alpha = ph + np.pi / kr                                        # outward direction of robot edge 0
+        a, b = Rr * np.cos(np.pi / kr), Ro * np.cos(np.pi / ko)         # inradii
+        robots.append(regular(kr, Rr, ph)); obstacles.append(regular(ko, Ro, alpha + np.pi - np.pi / ko))
+        px.append(-(a + b) * np.cos(alpha)); py.append(-(a + b) * np.sin(alpha))
+        sig.append(3e-5 * (Rr + Ro + a + b) * 10.0 ** rng.uniform(-1, 1))
+    sig = np.array(sig)
+    pp = satmc.make_poly_pairs(robots, obstacles, px, py, 0.0, sig, sig, 0.0)
+    n = 20_000
+    ctx.exact_evals(reset=True)
+    fast = poly_count(ctx, dev, pp, n=n, seed=4)
+    evals = ctx.exact_evals(reset=True)
+    exact = poly_count(ctx, dev, pp, n=n, seed=4, flags=EXACT)
+    np.testing.assert_array_equal(fast, exact)
+    frac = fast / n
+    assert ((frac > 0.2) & (frac < 0.8)).mean() > 0.8                  # the pairs really sit at first contact
+    assert 0.3 * pp.size * n < evals < 0.98 * pp.size * n              # some samples decided by the inscribed circles, most not
