@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Short driver for ncu: a few launches of one counting kernel.  usage: prof_fused.py [fused|fused5|streamed3|streamed5|ztest]"""
+"""Short driver for ncu: a few launches of one counting kernel.  usage: prof_fused.py [fused|fused5|streamed3|streamed5|ztest|sweep|poly]"""
 import importlib, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -15,6 +15,14 @@ if mode == "sweep":
     d_pairs = put(base); d_s = torch.from_numpy(sig.ravel()).cuda(); d_hits = torch.zeros(base.size * 64, dtype=torch.int64, device="cuda")
     for _ in range(3):
         ctx.count_fused_sweep(d_pairs, base.size, d_s, 64, 20_000, 7, d_hits)
+elif mode == "poly":
+    pr = wl.dataset_pairs(100_000, 3)
+    rv = lambda w, h: np.stack([-w / 2, -h / 2, w / 2, -h / 2, w / 2, h / 2, -w / 2, h / 2], 1).reshape(-1, 4, 2).astype(np.float32)
+    pp = satmc.make_poly_pairs(list(rv(pr["rw"], pr["rh"])), list(rv(pr["ow"], pr["oh"])), pr["rx"], pr["ry"], pr["rtheta"], pr["sd_x"], pr["sd_y"], pr["sd_theta"])
+    d_pairs = torch.from_numpy(np.ascontiguousarray(pp).view(np.uint8).view(np.float32)).cuda()
+    d_hits = torch.zeros(pp.size, dtype=torch.int64, device="cuda")
+    for _ in range(3):
+        ctx.count_fused_polygons(d_pairs, pp.size, 10_000, 7, d_hits)
 elif mode in ("fused", "fused5", "ztest"):
     pairs = wl.dataset_pairs(100_000, 3, shape_variance=(mode == "fused5"))
     n = 1000 if mode == "ztest" else 10_000
