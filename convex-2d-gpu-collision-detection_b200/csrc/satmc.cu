@@ -12,42 +12,18 @@
 #include <new>
 
 #include "satmc_kernels.cuh"
+#include "satmc_internal.hpp"
 
 // =============================================================================================
 // host side / C ABI
 // =============================================================================================
 using namespace satmc;
 
-struct satmc_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    int sm_count = 0;
-    int blocks_per_sm = 0;
-    int blocks_per_sm_streamed = 0;
-    int blocks_per_sm_tma[2] = {0, 0};       // bulk-copy staged streamed kernel, ndof 3 / 5
-    char err[512] = {0};
-    uint64_t launches = 0;
-    unsigned long long* d_exact_evals = nullptr;
-    // work-item counters of the dynamically scheduled kernels: never reset, the host mirrors their values (every processed
-    // item draws exactly one ticket).  Two of them: launches on the auxiliary stream (pipelined host calls) may run
-    // concurrently with launches on the main stream and must not share a counter.
-    unsigned long long* d_ticket = nullptr;
-    uint64_t ticket_next[2] = {0, 0};
-    int ticket_sel = 0;
-    SweepPlan* d_sweep_plan = nullptr;       // written by k_sweep_plan, read by both k_count_sweep variants
-    cudaStream_t aux = nullptr;              // pipelined host calls: second slice (created on first use)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool profiling = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float last_ms = 0.f;
-    bool last_ms_valid = false;
-    bool events_by_caller = false;           // a pipelined host call brackets both of its launches itself
-    // grow-only device scratch
-    void* d_scratch[3] = {nullptr, nullptr, nullptr};
-    size_t scratch_cap[3] = {0, 0, 0};
-};
-
-static thread_local char g_err[512] = {0};
+char* satmc_thread_error()
+{
+    static thread_local char e[512] = {0};
+    return e;
+}
 
 static inline size_t tma_smem_bytes(int ndof) { return (size_t)kWarps * kStages * ndof * kTile * sizeof(float); }
 
@@ -58,17 +34,16 @@ typedef CUresult (*tensor_map_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuui
 
 static tensor_map_encode_fn get_tensor_map_encode()
 {
-    static tensor_map_encode_fn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // initialised once, thread-safely (contexts are driven by one host thread each and may make their first
+    // streamed call at the same time)
+    static const tensor_map_encode_fn fn = [] {
         void* f = nullptr;
         cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<tensor_map_encode_fn>(f);
+        const bool ok = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+                        q == cudaDriverEntryPointSuccess;
         cudaGetLastError();
-    }
+        return ok ? reinterpret_cast<tensor_map_encode_fn>(f) : nullptr;
+    }();
     return fn;
 }
 
@@ -84,25 +59,6 @@ static bool make_z_tensor_map(CUtensorMap* map, const float* z, uint64_t ldz, in
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(z), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-
-static int fail(satmc_ctx* ctx, int code, const char* fmt, ...)
-{
-    char* dst = ctx ? ctx->err : g_err;
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(dst, 512, fmt, ap);
-    va_end(ap);
-    return code;
-}
-
-#define CU(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
-    return fail((ctx), SATMC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
 
 static int scratch(satmc_ctx* ctx, int slot, size_t bytes, void** out)
 {
@@ -123,7 +79,7 @@ extern "C" {
 
 const char* satmc_version(void) { return "satmc-b200 0.1 (sm_100a)"; }
 
-const char* satmc_last_error(const satmc_ctx* ctx) { return ctx ? ctx->err : g_err; }
+const char* satmc_last_error(const satmc_ctx* ctx) { return ctx ? ctx->err : satmc_thread_error(); }
 
 int satmc_create(int device, void* stream, satmc_ctx** out)
 {
@@ -164,13 +120,15 @@ int satmc_create(int device, void* stream, satmc_ctx** out)
     if (cudaMalloc(&ctx->d_exact_evals, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(ctx->d_exact_evals, 0, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&ctx->d_sweep_plan, sizeof(SweepPlan)) != cudaSuccess ||
-        cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(ctx->d_ticket, 0, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_ticket, 3 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(ctx->d_ticket, 0, 3 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_word, 64) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
         int rc = fail(nullptr, SATMC_ERR_CUDA, "context allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete ctx;
         return rc;
     }
+    ctx->d_blocks_done = reinterpret_cast<unsigned*>(ctx->d_ticket + 2);
     *out = ctx;
     return SATMC_OK;
 }
@@ -181,9 +139,11 @@ int satmc_destroy(satmc_ctx* ctx)
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 3; i++) if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
+    for (int i = 0; i < 2; i++) if (ctx->d_acc[i]) cudaFree(ctx->d_acc[i]);
     if (ctx->d_exact_evals) cudaFree(ctx->d_exact_evals);
     if (ctx->d_ticket) cudaFree(ctx->d_ticket);
     if (ctx->d_sweep_plan) cudaFree(ctx->d_sweep_plan);
+    if (ctx->h_word) cudaFreeHost(ctx->h_word);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -221,6 +181,8 @@ float satmc_last_kernel_ms(const satmc_ctx* ctx)
     return ms;
 }
 
+int satmc_plan_debug(satmc_ctx* ctx, int kind, uint64_t n_pairs, uint64_t n_samples, uint64_t* chunk_out, uint64_t* n_chunks_out);
+
 int satmc_exact_evals(satmc_ctx* ctx, uint64_t* out, int reset)
 {
     if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
@@ -238,9 +200,11 @@ int satmc_exact_evals(satmc_ctx* ctx, uint64_t* out, int reset)
 // Chooses the chunking of the sample range (work item = (pair, chunk), one warp per item) and the grid size.
 // items_per_warp: how many items a resident warp should get at least (when the sample range allows); the static
 // grid-stride assignment loses up to 1/items_per_warp of the run to the last, partly filled round.
-// max_chunk: upper bound on the samples of one item; 2^36 keeps the 32-bit per-lane counters exact (2^36 / 32 = 2^31).
+// max_chunk: upper bound on the samples of one item.  An item's hits are summed in 32 bits (per-lane counters, the
+// REDUX warp total, the sweep's per-setting shared-memory counters), so no item may exceed 2^31 samples.
+constexpr uint64_t kMaxChunk = 1ull << 31;
 static int plan_items(satmc_ctx* ctx, CountParams& p, int bps, uint64_t& blocks, int items_per_warp = 8,
-                      uint64_t max_chunk = 1ull << 36)
+                      uint64_t max_chunk = kMaxChunk)
 {
     const uint64_t resident_warps = (uint64_t)ctx->sm_count * bps * kWarps;
     const uint64_t target_items = resident_warps * (uint64_t)items_per_warp;
@@ -259,11 +223,13 @@ static int plan_items(satmc_ctx* ctx, CountParams& p, int bps, uint64_t& blocks,
             if (want > n_chunks) n_chunks = want;
         }
     }
+    if (max_chunk > kMaxChunk) max_chunk = kMaxChunk;
     const uint64_t per_chunk = (p.n_samples + n_chunks - 1) / n_chunks;
     if (per_chunk > max_chunk) n_chunks *= (per_chunk + max_chunk - 1) / max_chunk;   // a multiple: the rounds stay full
     if (n_chunks >= (uint64_t)kWarps) n_chunks = (n_chunks / kWarps) * kWarps;    // block-uniform pairs
     uint64_t chunk = (p.n_samples + n_chunks - 1) / n_chunks;
     chunk = ((chunk + 127) / 128) * 128;
+    if (chunk > kMaxChunk) chunk = kMaxChunk;                         // (a multiple of 128)
     n_chunks = (p.n_samples + chunk - 1) / chunk;
     if (n_chunks > 0xffffffffull) return fail(ctx, SATMC_ERR_INVALID, "too many chunks");
     p.chunk = chunk;
@@ -273,6 +239,23 @@ static int plan_items(satmc_ctx* ctx, CountParams& p, int bps, uint64_t& blocks,
     blocks = (p.n_items + kWarps - 1) / kWarps;
     const uint64_t max_blocks = (uint64_t)ctx->sm_count * bps;
     if (blocks > max_blocks) blocks = max_blocks;
+    return SATMC_OK;
+}
+
+// Diagnostics: the chunking the planner picks for a call of the given kind (0 fused rectangles, 1 streamed, 2 polygons,
+// 3 sweep) -- tests assert that no item exceeds 2^31 samples (32-bit per-item hit sums) without running 2^32-sample items.
+extern "C" int satmc_plan_debug(satmc_ctx* ctx, int kind, uint64_t n_pairs, uint64_t n_samples, uint64_t* chunk_out, uint64_t* n_chunks_out)
+{
+    if (!ctx || !chunk_out || !n_chunks_out) return fail(ctx, SATMC_ERR_INVALID, "null argument");
+    CountParams p{}; p.n_pairs = n_pairs; p.n_samples = n_samples;
+    uint64_t blocks = 0;
+    int rc;
+    if (kind == 0) rc = plan_items(ctx, p, ctx->blocks_per_sm, blocks, 8, 1ull << 20);
+    else if (kind == 1) rc = plan_items(ctx, p, ctx->blocks_per_sm_streamed, blocks);
+    else if (kind == 2) rc = plan_items(ctx, p, 2, blocks);
+    else rc = plan_items(ctx, p, 2, blocks, 32);
+    if (rc) return rc;
+    *chunk_out = p.chunk; *n_chunks_out = p.n_chunks;
     return SATMC_OK;
 }
 
@@ -290,12 +273,40 @@ static void use_tickets(satmc_ctx* ctx, CountParams& p, uint64_t blocks)
     ctx->ticket_next[ctx->ticket_sel] += p.n_items;
 }
 
-// With several chunks per pair the kernels accumulate with atomics: the counters must start from zero unless the
-// caller asked to accumulate.  `counters` = number of 64-bit counters behind p.hits.
-static int clear_hits_for_atomics(satmc_ctx* ctx, const CountParams& p, uint64_t counters, uint32_t user_flags)
+// With several work items per counter the kernels accumulate with atomics.  Instead of clearing the caller's counters
+// first (a second launch: 2-3 us for a memset node plus the gap to the kernel, as much as a whole cfg 2 call), the
+// atomics go to a scratch array of the context that holds zeros between launches; the last block to finish moves the
+// totals to the caller's array (or adds them, SATMC_ACCUMULATE) and zeroes the scratch again (finalize_counters).
+// `span` = counters behind p.hits, of which this launch owns `counters`, laid out as fin_inner consecutive ones every
+// fin_stride.
+static int prepare_counters(satmc_ctx* ctx, CountParams& p, uint64_t span, uint64_t counters, uint64_t fin_inner = 1,
+                            uint64_t fin_stride = 1, uint64_t acc_offset = 0)
 {
-    if (p.n_chunks > 1 && !(user_flags & SATMC_ACCUMULATE))
-        CU(ctx, cudaMemsetAsync(p.hits, 0, counters * sizeof(unsigned long long), ctx->stream));
+    p.hits_len = span - acc_offset;
+    p.acc = nullptr; p.blocks_done = nullptr;
+    if (p.n_chunks <= 1) return SATMC_OK;
+    const int sel = ctx->ticket_sel;
+    if (span > ctx->acc_cap[sel]) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(ctx->stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+            cudaGetLastError();
+            return fail(ctx, SATMC_ERR_INVALID, "the accumulator scratch must grow, which cannot be captured: make one call of "
+                                                "this size before capturing");
+        }
+        // launches that still use the old array must finish before it is freed
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_acc[sel]) { CU(ctx, cudaFree(ctx->d_acc[sel])); ctx->d_acc[sel] = nullptr; ctx->acc_cap[sel] = 0; }
+        const size_t cap_n = (size_t)(span + span / 4 + 64);
+        if (cudaMalloc(&ctx->d_acc[sel], cap_n * sizeof(unsigned long long)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, SATMC_ERR_NOMEM, "cudaMalloc of %zu bytes failed", cap_n * sizeof(unsigned long long));
+        }
+        CU(ctx, cudaMemset(ctx->d_acc[sel], 0, cap_n * sizeof(unsigned long long)));
+        ctx->acc_cap[sel] = cap_n;
+    }
+    p.acc = ctx->d_acc[sel] + acc_offset;
+    p.blocks_done = ctx->d_blocks_done + sel;
+    p.n_counters = counters; p.fin_inner = fin_inner; p.fin_stride = fin_stride;
     return SATMC_OK;
 }
 
@@ -321,7 +332,7 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
     int rc = plan_items(ctx, p, bps, blocks, 8, STREAMED ? (1ull << 36) : (1ull << 20));
     if (rc) return rc;
     const bool defer = !STREAMED && p.chunk >= 32768;
-    rc = clear_hits_for_atomics(ctx, p, p.n_pairs, p.flags);
+    rc = prepare_counters(ctx, p, p.n_pairs, p.n_pairs);
     if (rc) return rc;
     const uint64_t ticket_before = ctx->ticket_next[ctx->ticket_sel];
     // bulk-copy staged kernel: dynamic order only when all pairs read one shared bank (L2 resident, issue bound: +5 %);
@@ -369,7 +380,7 @@ int satmc_count_fused(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pair
     if (n_pairs > 0xffffffffull - pair_id_offset) return fail(ctx, SATMC_ERR_INVALID, "pair ids exceed 32 bits");
     if (((uintptr_t)d_pairs & 15u) != 0) return fail(ctx, SATMC_ERR_INVALID, "d_pairs must be 16-byte aligned");
     DeviceGuard g(ctx->device);
-    CountParams p{};
+    CountParams p{}; p.pair_id_stride = 1;
     p.n_pairs = n_pairs; p.n_samples = n_samples; p.sample_offset = sample_offset; p.pair_id_offset = pair_id_offset;
     philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), p.keys); p.flags = flags;
     p.hits = reinterpret_cast<unsigned long long*>(d_hits); p.exact_evals = ctx->d_exact_evals;
@@ -383,7 +394,7 @@ int satmc_count_streamed(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_p
     if (rc) return rc;
     if (((uintptr_t)d_pairs & 15u) != 0) return fail(ctx, SATMC_ERR_INVALID, "d_pairs must be 16-byte aligned");
     DeviceGuard g(ctx->device);
-    CountParams p{};
+    CountParams p{}; p.pair_id_stride = 1;
     p.n_pairs = n_pairs; p.n_samples = n_samples; p.flags = flags;
     p.hits = reinterpret_cast<unsigned long long*>(d_hits); p.exact_evals = ctx->d_exact_evals;
     p.z = d_z; p.ldz = ldz; p.z_pair_stride = z_pair_stride; p.ndof = ndof;
@@ -473,7 +484,7 @@ int satmc_count_fused_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs, u
     if ((!d_pairs || !d_hits) && n_pairs) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
     if (n_pairs > 0xffffffffull - pair_id_offset) return fail(ctx, SATMC_ERR_INVALID, "pair ids exceed 32 bits");
     DeviceGuard g(ctx->device);
-    CountParams p{};
+    CountParams p{}; p.pair_id_stride = 1;
     p.n_pairs = n_pairs; p.n_samples = n_samples; p.sample_offset = sample_offset; p.pair_id_offset = pair_id_offset;
     philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), p.keys); p.flags = flags & (SATMC_ACCUMULATE | SATMC_EXACT_ONLY); p.exact_evals = ctx->d_exact_evals;
     p.hits = reinterpret_cast<unsigned long long*>(d_hits);
@@ -484,7 +495,7 @@ int satmc_count_fused_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs, u
     uint64_t blocks = 0;
     int rc = plan_items(ctx, p, 2, blocks);
     if (rc) return rc;
-    rc = clear_hits_for_atomics(ctx, p, n_pairs, flags);
+    rc = prepare_counters(ctx, p, n_pairs, n_pairs);
     if (rc) return rc;
     const uint64_t ticket_before = ctx->ticket_next[ctx->ticket_sel];
     use_tickets(ctx, p, blocks);
@@ -501,7 +512,7 @@ int satmc_count_streamed_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs
     int rc = check_streamed_args(ctx, d_pairs, d_z, ldz, 3, n_samples, n_pairs, z_pair_stride, d_hits);
     if (rc) return rc;
     DeviceGuard g(ctx->device);
-    CountParams p{};
+    CountParams p{}; p.pair_id_stride = 1;
     p.n_pairs = n_pairs; p.n_samples = n_samples; p.flags = flags & (SATMC_ACCUMULATE | SATMC_EXACT_ONLY); p.exact_evals = ctx->d_exact_evals;
     p.hits = reinterpret_cast<unsigned long long*>(d_hits);
     p.z = d_z; p.ldz = ldz; p.z_pair_stride = z_pair_stride; p.ndof = 3;
@@ -512,7 +523,7 @@ int satmc_count_streamed_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs
     uint64_t blocks = 0;
     rc = plan_items(ctx, p, 2, blocks);
     if (rc) return rc;
-    rc = clear_hits_for_atomics(ctx, p, n_pairs, flags);
+    rc = prepare_counters(ctx, p, n_pairs, n_pairs);
     if (rc) return rc;
     const uint64_t ticket_before = ctx->ticket_next[ctx->ticket_sel];
     use_tickets(ctx, p, blocks);
@@ -523,12 +534,12 @@ int satmc_count_streamed_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs
     return SATMC_OK;
 }
 
-int satmc_count_fused_sweep(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pairs, const float* d_sigmas, uint32_t n_cov,
+int satmc_count_fused_sweep(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pairs, const float* h_sigmas, uint32_t n_cov,
                             uint64_t n_samples, uint64_t seed, uint64_t sample_offset, uint32_t pair_id_offset, uint64_t* d_hits,
                             uint32_t flags)
 {
     if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
-    if ((!d_pairs || !d_hits || !d_sigmas) && n_pairs && n_cov) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
+    if ((!d_pairs || !d_hits || !h_sigmas) && n_pairs && n_cov) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
     if (n_pairs > 0xffffffffull - pair_id_offset) return fail(ctx, SATMC_ERR_INVALID, "pair ids exceed 32 bits");
     if (((uintptr_t)d_pairs & 15u) != 0) return fail(ctx, SATMC_ERR_INVALID, "d_pairs must be 16-byte aligned");
     if (n_pairs == 0 || n_cov == 0) return SATMC_OK;
@@ -537,7 +548,7 @@ int satmc_count_fused_sweep(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t 
         if (!(flags & SATMC_ACCUMULATE)) CU(ctx, cudaMemsetAsync(d_hits, 0, n_pairs * n_cov * sizeof(uint64_t), ctx->stream));
         return SATMC_OK;
     }
-    CountParams p{};
+    CountParams p{}; p.pair_id_stride = 1;
     p.n_pairs = n_pairs; p.n_samples = n_samples; p.sample_offset = sample_offset; p.pair_id_offset = pair_id_offset;
     philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), p.keys);
     p.flags = flags;
@@ -545,13 +556,18 @@ int satmc_count_fused_sweep(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t 
     uint64_t blocks = 0;
     int rc = plan_items(ctx, p, 2, blocks, 32);          // an item costs n_cov x a plain one: cut finer (+7 % on cfg5)
     if (rc) return rc;
-    rc = clear_hits_for_atomics(ctx, p, n_pairs * n_cov, flags);
+    void* d_sig = nullptr;
+    rc = scratch(ctx, 2, 3 * (size_t)n_cov * sizeof(float), &d_sig);
     if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(d_sig, h_sigmas, 3 * (size_t)n_cov * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    const float* d_sigmas = static_cast<const float*>(d_sig);
     // settings are processed kSweepMax at a time; every slice sees the same normals
     for (uint32_t c0 = 0; c0 < n_cov; c0 += kSweepMax) {
         const int nc = (int)((n_cov - c0 < (uint32_t)kSweepMax) ? n_cov - c0 : kSweepMax);
         CountParams q = p;
         q.hits = p.hits + c0;
+        rc = prepare_counters(ctx, q, n_pairs * n_cov, n_pairs * (uint64_t)nc, (uint64_t)nc, (uint64_t)n_cov, c0);
+        if (rc) return rc;
         k_sweep_plan<<<1, kSweepMax, 0, ctx->stream>>>(d_sigmas + 3 * (size_t)c0, nc, ctx->d_sweep_plan);
         k_count_sweep<false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(d_pairs, d_sigmas + 3 * (size_t)c0, nc, (uint64_t)n_cov, q,
                                                                             ctx->d_sweep_plan);
@@ -563,11 +579,16 @@ int satmc_count_fused_sweep(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t 
     return SATMC_OK;
 }
 
+}  // extern "C"
+
+// One step of the reference kernel contract: count n_batch more samples for the first num_left slots, then the
+// z-test tail.  With `ar` (adaptive run) the tail also retires finished pairs and compacts the live list in the same
+// kernel; without it the tail is the reference kernel's own (done flags, running counts).
 static int mc_step_impl(satmc_ctx* ctx, const float* d_robot_base, const float* d_poses, uint32_t n_poses,
                         const float* d_std_devs, uint32_t n_std, const float* d_pose_idxs, const float* d_std_dev_idxs,
                         const float* d_positions, float* d_cps, const float* d_accuracy_bins, const float* d_bin_accuracy,
                         int n_accuracy_bins, int* d_done, int n_samples, int n_batch, int num_left, uint64_t seed,
-                        uint32_t stream_id_offset, const int* d_live)
+                        uint32_t stream_id_offset, uint32_t stream_id_stride, const int* d_live, AdaptiveRun* ar)
 {
     if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
     if (!d_robot_base || !d_poses || !d_std_devs || !d_pose_idxs || !d_std_dev_idxs || !d_positions || !d_cps ||
@@ -577,25 +598,107 @@ static int mc_step_impl(satmc_ctx* ctx, const float* d_robot_base, const float* 
         return fail(ctx, SATMC_ERR_INVALID, "bad sizes (n_batch %d, n_samples %d, num_left %d, bins %d)", n_batch, n_samples,
                     num_left, n_accuracy_bins);
     if (num_left == 0) return SATMC_OK;
+    // Philox stream ids are 32 bits: ids of the slots must not wrap (two rows 2^32 apart would share a stream)
+    const uint64_t span = ar ? (uint64_t)ar->n_pairs : (uint64_t)num_left;
+    if ((span - 1) * (uint64_t)stream_id_stride > 0xffffffffull - stream_id_offset)
+        return fail(ctx, SATMC_ERR_INVALID, "Philox stream ids exceed 32 bits (offset %u, %llu slots, stride %u)", stream_id_offset,
+                    (unsigned long long)span, stream_id_stride);
     DeviceGuard g(ctx->device);
     void* d_hits = nullptr;
     int rc = scratch(ctx, 0, (size_t)num_left * sizeof(unsigned long long), &d_hits);
     if (rc) return rc;
-    CountParams p{};
+    CountParams p{}; p.pair_id_stride = stream_id_stride;
     p.n_pairs = (uint64_t)num_left; p.n_samples = (uint64_t)n_batch; p.sample_offset = (uint64_t)(n_samples - n_batch);
     p.pair_id_offset = stream_id_offset; philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), p.keys); p.flags = 0;
     p.hits = reinterpret_cast<unsigned long long*>(d_hits); p.exact_evals = ctx->d_exact_evals;
     IndirectSrc src{d_robot_base, d_poses, d_std_devs, d_pose_idxs, d_std_dev_idxs, d_positions, n_poses, n_std, d_live};
-    if (n_batch == 0) CU(ctx, cudaMemsetAsync(d_hits, 0, (size_t)num_left * sizeof(unsigned long long), ctx->stream));
     rc = launch_count<IndirectSrc, false>(ctx, src, p, ctx->profiling);
     if (rc) return rc;
-    k_ztest_tail<<<(num_left + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<unsigned long long*>(d_hits), d_cps,
-                                                                   d_accuracy_bins, d_bin_accuracy, n_accuracy_bins, d_done,
-                                                                   n_samples, num_left, d_live);
+    if (ar) {
+        k_ztest_compact<<<(num_left + 255) / 256, 256, 0, ctx->stream>>>(
+            reinterpret_cast<unsigned long long*>(d_hits), d_cps, d_accuracy_bins, d_bin_accuracy, n_accuracy_bins, n_samples, num_left,
+            d_live, ar->d_cp_out, ar->d_n_samples_out, ar->d_live[ar->cur ^ 1], ar->d_n + (ar->iter & 1), ar->d_n + ((ar->iter + 1) & 1),
+            ar->n_pairs);
+    } else {
+        k_ztest_tail<<<(num_left + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<unsigned long long*>(d_hits), d_cps,
+                                                                       d_accuracy_bins, d_bin_accuracy, n_accuracy_bins, d_done,
+                                                                       n_samples, num_left, d_live);
+    }
     CU(ctx, cudaGetLastError());
     ctx->launches++;
     return SATMC_OK;
 }
+
+// ---- the adaptive loop in steps, so that a group can drive several devices in lockstep from one host thread ----
+int satmc_adaptive_begin(AdaptiveRun& ar)
+{
+    satmc_ctx* ctx = ar.ctx;
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    if (!ar.d_cp_out) return fail(ctx, SATMC_ERR_INVALID, "d_cp_out is NULL");
+    if (ar.n_pairs < 0 || ar.n_batch_small <= 0 || ar.n_batch_large <= 0 || ar.max_samples <= 0 || ar.stream_id_stride == 0)
+        return fail(ctx, SATMC_ERR_INVALID, "bad schedule (n_pairs %d, n_batch %d/%d, max_samples %d)", ar.n_pairs, ar.n_batch_small,
+                    ar.n_batch_large, ar.max_samples);
+    ar.num_left = ar.n_pairs; ar.n_samples = 0; ar.iter = 0; ar.cur = 0; ar.drawn = 0;
+    if (ar.n_pairs == 0) return SATMC_OK;
+    DeviceGuard g(ctx->device);
+    // work buffers: counts (float, as the reference keeps them), two live lists, two counters
+    const size_t n = (size_t)ar.n_pairs;
+    void* base = nullptr;
+    int rc = scratch(ctx, 1, n * (sizeof(float) + 2 * sizeof(int)) + 256, &base);
+    if (rc) return rc;
+    ar.d_counts = reinterpret_cast<float*>(base);
+    ar.d_live[0] = reinterpret_cast<int*>(ar.d_counts + n);
+    ar.d_live[1] = ar.d_live[0] + n;
+    ar.d_n = ar.d_live[1] + n;
+    CU(ctx, cudaMemsetAsync(ar.d_counts, 0, n * sizeof(float), ctx->stream));
+    CU(ctx, cudaMemsetAsync(ar.d_n, 0, 2 * sizeof(int), ctx->stream));
+    k_iota<<<(ar.n_pairs + 255) / 256, 256, 0, ctx->stream>>>(ar.d_live[0], ar.n_pairs);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    return SATMC_OK;
+}
+
+bool satmc_adaptive_pending(const AdaptiveRun& ar) { return ar.num_left > 0 && ar.n_samples < ar.max_samples; }
+
+// one iteration, asynchronous; the number of pairs still unfinished arrives in the context's pinned word
+int satmc_adaptive_enqueue(AdaptiveRun& ar)
+{
+    satmc_ctx* ctx = ar.ctx;
+    const int n_batch = (ar.n_samples < ar.switch_at) ? ar.n_batch_small : ar.n_batch_large;    // generate_dataset.cu:427-430
+    ar.n_samples += n_batch;
+    int rc = mc_step_impl(ctx, ar.d_robot_base, ar.d_poses, ar.n_poses, ar.d_std_devs, ar.n_std, ar.d_pose_idxs, ar.d_std_dev_idxs,
+                          ar.d_positions, ar.d_counts, ar.d_bins, ar.d_bin_acc, ar.n_bins, /*d_done (unused)*/ ar.d_live[0],
+                          ar.n_samples, n_batch, ar.num_left, ar.seed, ar.stream_id_offset, ar.stream_id_stride, ar.d_live[ar.cur], &ar);
+    if (rc) return rc;
+    DeviceGuard g(ctx->device);
+    ar.drawn += (long long)ar.num_left * n_batch;
+    CU(ctx, cudaMemcpyAsync(ctx->h_word, ar.d_n + (ar.iter & 1), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return SATMC_OK;
+}
+
+// after the stream has been synchronised
+void satmc_adaptive_collect(AdaptiveRun& ar)
+{
+    ar.num_left = *ar.ctx->h_word;
+    ar.cur ^= 1;
+    ar.iter++;
+}
+
+// pairs that hit max_samples: count / n_samples as they stand (ztest.cu:376-385)
+int satmc_adaptive_finish(AdaptiveRun& ar)
+{
+    satmc_ctx* ctx = ar.ctx;
+    if (ar.num_left <= 0) return SATMC_OK;
+    DeviceGuard g(ctx->device);
+    k_compact_live<<<(ar.num_left + 255) / 256, 256, 0, ctx->stream>>>(ar.d_live[ar.cur], ar.num_left, ar.d_counts, ar.n_samples,
+                                                                          ar.d_cp_out, ar.d_n_samples_out, ar.n_pairs);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    ar.num_left = 0;
+    return SATMC_OK;
+}
+
+extern "C" {
 
 int satmc_mc_step(satmc_ctx* ctx, const float* d_robot_base, const float* d_poses, uint32_t n_poses, const float* d_std_devs,
                   uint32_t n_std, const float* d_pose_idxs, const float* d_std_dev_idxs, const float* d_positions,
@@ -606,7 +709,7 @@ int satmc_mc_step(satmc_ctx* ctx, const float* d_robot_base, const float* d_pose
     (void)iteration;
     return mc_step_impl(ctx, d_robot_base, d_poses, n_poses, d_std_devs, n_std, d_pose_idxs, d_std_dev_idxs, d_positions,
                         d_cps, d_accuracy_bins, d_bin_accuracy, n_accuracy_bins, d_done, n_samples, n_batch, num_left, seed,
-                        stream_id_offset, nullptr);
+                        stream_id_offset, 1u, nullptr, nullptr);
 }
 
 int satmc_adaptive_run(satmc_ctx* ctx, const float* d_robot_base, const float* d_poses, uint32_t n_poses,
@@ -616,58 +719,27 @@ int satmc_adaptive_run(satmc_ctx* ctx, const float* d_robot_base, const float* d
                        uint64_t seed, uint32_t stream_id_offset, float* d_cp_out, int* d_n_samples_out,
                        int* iterations_out, long long* samples_drawn_out)
 {
-    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
-    if (!d_cp_out) return fail(ctx, SATMC_ERR_INVALID, "d_cp_out is NULL");
-    if (n_pairs < 0 || n_batch_small <= 0 || n_batch_large <= 0 || max_samples <= 0)
-        return fail(ctx, SATMC_ERR_INVALID, "bad schedule (n_pairs %d, n_batch %d/%d, max_samples %d)", n_pairs, n_batch_small,
-                    n_batch_large, max_samples);
     if (iterations_out) *iterations_out = 0;
     if (samples_drawn_out) *samples_drawn_out = 0;
-    if (n_pairs == 0) return SATMC_OK;
-    DeviceGuard g(ctx->device);
-    // work buffers: counts (float, as the reference keeps them), done flags, two live lists, a counter
-    const size_t n = (size_t)n_pairs;
-    void* base = nullptr;
-    const size_t bytes = n * (sizeof(float) + 3 * sizeof(int)) + 256;
-    int rc = scratch(ctx, 1, bytes, &base);
+    AdaptiveRun ar{};
+    ar.ctx = ctx; ar.d_robot_base = d_robot_base; ar.d_poses = d_poses; ar.n_poses = n_poses; ar.d_std_devs = d_std_devs; ar.n_std = n_std;
+    ar.d_pose_idxs = d_pose_idxs; ar.d_std_dev_idxs = d_std_dev_idxs; ar.d_positions = d_positions; ar.n_pairs = n_pairs;
+    ar.d_bins = d_accuracy_bins; ar.d_bin_acc = d_bin_accuracy; ar.n_bins = n_accuracy_bins; ar.max_samples = max_samples;
+    ar.n_batch_small = n_batch_small; ar.switch_at = switch_at; ar.n_batch_large = n_batch_large; ar.seed = seed;
+    ar.stream_id_offset = stream_id_offset; ar.stream_id_stride = 1; ar.d_cp_out = d_cp_out; ar.d_n_samples_out = d_n_samples_out;
+    int rc = satmc_adaptive_begin(ar);
     if (rc) return rc;
-    float* d_counts = reinterpret_cast<float*>(base);
-    int* d_done = reinterpret_cast<int*>(d_counts + n);
-    int* d_live[2] = {d_done + n, d_done + 2 * n};
-    int* d_n = d_done + 3 * n;
-    CU(ctx, cudaMemsetAsync(d_counts, 0, n * sizeof(float), ctx->stream));
-    k_iota<<<(n_pairs + 255) / 256, 256, 0, ctx->stream>>>(d_live[0], n_pairs);
-    CU(ctx, cudaGetLastError());
-    ctx->launches++;
-    int num_left = n_pairs, n_samples = 0, iter = 0, cur = 0;
-    long long drawn = 0;
-    while (num_left > 0 && n_samples < max_samples) {                       // ztest.cu:328, generate_dataset.cu:425
-        const int n_batch = (n_samples < switch_at) ? n_batch_small : n_batch_large;    // generate_dataset.cu:427-430
-        n_samples += n_batch;
-        rc = mc_step_impl(ctx, d_robot_base, d_poses, n_poses, d_std_devs, n_std, d_pose_idxs, d_std_dev_idxs, d_positions,
-                          d_counts, d_accuracy_bins, d_bin_accuracy, n_accuracy_bins, d_done, n_samples, n_batch, num_left,
-                          seed, stream_id_offset, d_live[cur]);
+    while (satmc_adaptive_pending(ar)) {                                    // ztest.cu:328, generate_dataset.cu:425
+        rc = satmc_adaptive_enqueue(ar);
         if (rc) return rc;
-        drawn += (long long)num_left * n_batch;
-        CU(ctx, cudaMemsetAsync(d_n, 0, sizeof(int), ctx->stream));
-        k_compact_live<<<(num_left + 255) / 256, 256, 0, ctx->stream>>>(d_live[cur], num_left, d_done, d_counts, n_samples,
-                                                                         d_cp_out, d_n_samples_out, d_live[cur ^ 1], d_n, 0);
-        CU(ctx, cudaGetLastError());
-        ctx->launches++;
-        CU(ctx, cudaMemcpyAsync(&num_left, d_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        DeviceGuard g(ctx->device);
         CU(ctx, cudaStreamSynchronize(ctx->stream));                       // the loop condition needs the count
-        cur ^= 1;
-        iter++;
+        satmc_adaptive_collect(ar);
     }
-    if (num_left > 0) {                                                     // hit max_samples: ztest.cu:376-385
-        CU(ctx, cudaMemsetAsync(d_n, 0, sizeof(int), ctx->stream));
-        k_compact_live<<<(num_left + 255) / 256, 256, 0, ctx->stream>>>(d_live[cur], num_left, d_done, d_counts, n_samples,
-                                                                         d_cp_out, d_n_samples_out, d_live[cur ^ 1], d_n, 1);
-        CU(ctx, cudaGetLastError());
-        ctx->launches++;
-    }
-    if (iterations_out) *iterations_out = iter;
-    if (samples_drawn_out) *samples_drawn_out = drawn;
+    rc = satmc_adaptive_finish(ar);
+    if (rc) return rc;
+    if (iterations_out) *iterations_out = ar.iter;
+    if (samples_drawn_out) *samples_drawn_out = ar.drawn;
     return SATMC_OK;
 }
 
@@ -727,6 +799,16 @@ int satmc_download(satmc_ctx* ctx, void* h_dst, const void* d_src, size_t bytes)
     DeviceGuard g(ctx->device);
     CU(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SATMC_OK;
+}
+
+int satmc_download_async(satmc_ctx* ctx, void* h_dst, const void* d_src, size_t bytes)
+{
+    if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
+    if (bytes == 0) return SATMC_OK;
+    if (!h_dst || !d_src) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
+    DeviceGuard g(ctx->device);
+    CU(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return SATMC_OK;
 }
 

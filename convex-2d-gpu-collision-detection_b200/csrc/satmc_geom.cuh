@@ -21,6 +21,17 @@
 #include <stdint.h>
 #include <math_constants.h>
 
+// -DSATMC_DEBUG (libsatmc_debug.so): every indexed device-side write is bounds-checked; a violation prints
+// the site and traps, which the host sees as a launch failure.  compute-sanitizer is not available on the
+// GPU pool this library is developed on, so this build is run through the whole GPU test suite instead.
+#ifdef SATMC_DEBUG
+#include <cstdio>
+#define SATMC_ASSERT(cond) do { if (!(cond)) { printf("SATMC_ASSERT failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, \
+                                                        (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
+#else
+#define SATMC_ASSERT(cond) ((void)0)
+#endif
+
 namespace satmc {
 
 // Bound on |z| under which the screening threshold is valid.  The fused sampler cannot exceed 6.77
@@ -31,19 +42,22 @@ namespace satmc {
 // exact reference arithmetic
 // ---------------------------------------------------------------------------------------------
 
-// create_rect(w,h) [utils.cu:119-130] + rot_trans_rectangle(pos, theta) [utils.cu:132-142] for the
-// robot (ztest.cu:148-149,297):  x' = FADD(FFMA(x,c,-FMUL(y,s)), px)   y' = FADD(FFMA(x,s,FMUL(y,c)), py)
-__device__ __forceinline__ void exact_robot_corners(float px, float py, float c, float s, float rw, float rh,
-                                                    float r[8])
+// create_rect(w,h) [utils.cu:119-130]: corners counter-clockwise from (-w/2, -h/2), AoS x0,y0..x3,y3
+__device__ __forceinline__ void rect_base(float w, float h, float b[8])
 {
-    // c, s = cosf(pose.theta), sinf(pose.theta): the precise libdevice values (PairConst::ca, sa)
-    const float hx = rw / 2, hy = rh / 2;
-    const float bx[4] = {-hx, hx, hx, -hx};
-    const float by[4] = {-hy, -hy, hy, hy};
+    const float hx = w / 2, hy = h / 2;
+    b[0] = -hx; b[1] = -hy; b[2] = hx; b[3] = -hy; b[4] = hx; b[5] = hy; b[6] = -hx; b[7] = hy;
+}
+
+// rot_trans_rectangle(pos, theta) [utils.cu:132-142] applied to the robot base quad (ztest.cu:148-149,297):
+//   x' = FADD(FFMA(x,c,-FMUL(y,s)), px)   y' = FADD(FFMA(x,s,FMUL(y,c)), py)
+// c, s = cosf(pose.theta), sinf(pose.theta): the precise libdevice values (PairConst::ca, sa)
+__device__ __forceinline__ void exact_robot_corners(float px, float py, float c, float s, const float base[8], float r[8])
+{
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        r[2 * i]     = __fadd_rn(__fmaf_rn(bx[i], c, -__fmul_rn(by[i], s)), px);
-        r[2 * i + 1] = __fadd_rn(__fmaf_rn(bx[i], s, __fmul_rn(by[i], c)), py);
+        r[2 * i]     = __fadd_rn(__fmaf_rn(base[2 * i], c, -__fmul_rn(base[2 * i + 1], s)), px);
+        r[2 * i + 1] = __fadd_rn(__fmaf_rn(base[2 * i], s, __fmul_rn(base[2 * i + 1], c)), py);
     }
 }
 

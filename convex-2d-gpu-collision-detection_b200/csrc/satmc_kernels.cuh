@@ -45,6 +45,9 @@ constexpr int kWarps = kThreads / 32;
 struct DirectSrc {
     const satmc_pair* pairs;
     __device__ __forceinline__ uint64_t element(uint64_t slot) const { return slot; }
+    // the robot is create_rect(rw, rh) by construction: the screening pass always applies
+    __device__ __forceinline__ bool robot_is_centred_rect() const { return true; }
+    __device__ __forceinline__ void robot_base8(const float v[12], float b[8]) const { rect_base(v[3], v[4], b); }
     __device__ __forceinline__ void load(uint64_t i, float v[12]) const {
         const float4* p = reinterpret_cast<const float4*>(pairs + i);   // 48 B, 16-B aligned
         const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
@@ -61,6 +64,19 @@ struct IndirectSrc {
     uint32_t n_poses, n_std;
     const int* live;               // optional: slot -> pair id (device-side work list of unfinished pairs)
     __device__ __forceinline__ uint64_t element(uint64_t slot) const { return live ? (uint64_t)__ldg(live + slot) : slot; }
+    // The reference kernel transforms whatever 8 floats robot_base holds (ztest.cu:148-149).  Its mains always upload
+    // create_rect(robot_w, robot_h) (ztest.cu:297), which is what the screening pass assumes (centre / half extents);
+    // any other quad is honoured by evaluating every sample of the launch with the exact arithmetic on the 8 corners
+    // as given (slow, same results as the reference).
+    __device__ __forceinline__ bool robot_is_centred_rect() const {
+        const float x0 = __ldg(robot_base), y0 = __ldg(robot_base + 1), x1 = __ldg(robot_base + 2), y1 = __ldg(robot_base + 3);
+        const float x2 = __ldg(robot_base + 4), y2 = __ldg(robot_base + 5), x3 = __ldg(robot_base + 6), y3 = __ldg(robot_base + 7);
+        return x0 == -x1 && y0 == -y2 && y1 == y0 && x2 == x1 && x3 == x0 && y3 == y2 && x1 >= 0.0f && y2 >= 0.0f;
+    }
+    __device__ __forceinline__ void robot_base8(const float*, float b[8]) const {
+#pragma unroll
+        for (int k = 0; k < 8; k++) b[k] = __ldg(robot_base + k);
+    }
     __device__ __forceinline__ void load(uint64_t i, float v[12]) const {
         uint32_t pi = (uint32_t)(int)__ldg(pose_idxs + i);
         uint32_t si = (uint32_t)(int)__ldg(std_dev_idxs + i);
@@ -94,7 +110,41 @@ struct CountParams {
     // dynamic work distribution (null = static grid-stride): a warp's first item is its global warp index, every further
     // one is drawn from a device counter that only ever grows; ticket_base is its value when this launch starts
     unsigned long long* ticket; unsigned long long ticket_base;
+    // Philox stream of array element e = pair_id_offset + e * pair_id_stride (stride > 1: rows dealt round-robin to GPUs)
+    uint32_t pair_id_stride;
+    // Several work items per counter (n_chunks > 1): contributions are added atomically to `acc`, a scratch array of
+    // the context that holds zeros between launches, and the last block to finish moves the totals to `hits` and
+    // leaves `acc` and `blocks_done` zero again -- one launch, no memset (finalize_counters).  Counter i of the launch
+    // lives at offset (i / fin_inner) * fin_stride + i % fin_inner of both arrays (sweep: one slice of the settings).
+    unsigned long long* acc; unsigned* blocks_done;
+    uint64_t n_counters, fin_inner, fin_stride;
+    uint64_t hits_len;         // counters behind `hits` (and `acc`): bounds for the -DSATMC_DEBUG build
 };
+
+// where the atomics of a launch go
+__device__ __forceinline__ unsigned long long* counter_base(const CountParams& p) { return p.acc ? p.acc : p.hits; }
+
+// End of every counting kernel.  All threads of the block must call it (it contains barriers).
+__device__ __forceinline__ void finalize_counters(const CountParams& p)
+{
+    if (p.acc == nullptr) return;                                     // launch-uniform
+    __shared__ unsigned s_last;
+    __syncthreads();                                                  // this block's atomics are issued
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(p.blocks_done, 1u) == gridDim.x - 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();                                                  // every other block's atomics are visible
+    for (uint64_t i = threadIdx.x; i < p.n_counters; i += blockDim.x) {
+        const uint64_t off = (i / p.fin_inner) * p.fin_stride + i % p.fin_inner;
+        const unsigned long long v = atomicExch(p.acc + off, 0ull);
+        SATMC_ASSERT(off < p.hits_len);
+        if (p.flags & SATMC_ACCUMULATE) p.hits[off] += v; else p.hits[off] = v;
+    }
+    if (threadIdx.x == 0) *p.blocks_done = 0u;
+}
 
 // Next work item of a warp.  `drawn` is the ticket lane 0 took while the warp was busy with the current item.
 __device__ __forceinline__ uint64_t next_item(const CountParams& p, uint64_t item, uint64_t stride, unsigned long long drawn)
@@ -331,12 +381,15 @@ __device__ __noinline__ void cold_flush(ColdQueue* Qp, const Src& src, const Cou
         src.load(elem, v);
         PairConst P;
         pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
-        float robot[8];
-        exact_robot_corners(v[0], v[1], P.ca, P.sa, v[3], v[4], robot);
-        const uint32_t pid = p.pair_id_offset + (uint32_t)elem;
+        float robot[8], base[8];
+        src.robot_base8(v, base);
+        exact_robot_corners(v[0], v[1], P.ca, P.sa, base, robot);
+        if (!src.robot_is_centred_rect()) { P.eps = CUDART_INF_F; P.eps_b = CUDART_INF_F; }
+        const uint32_t pid = p.pair_id_offset + (uint32_t)elem * p.pair_id_stride;
         const unsigned c = (v[10] == 0.0f && v[11] == 0.0f) ? fused_group_slow<3>(P, robot, g, 0xFu, pid, p.keys, p.exact_evals)
                                                            : fused_group_slow<5>(P, robot, g, 0xFu, pid, p.keys, p.exact_evals);
-        if (c) atomicAdd(p.hits + slot, (unsigned long long)c);
+        SATMC_ASSERT(slot < p.hits_len);
+        if (c) atomicAdd(counter_base(p) + slot, (unsigned long long)c);
     }
     __syncwarp();
     if (lane == 0) Q.n = 0;
@@ -364,21 +417,27 @@ __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED
         src.load(elem, v);
         PairConst P;
         pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
-        if (p.flags & SATMC_EXACT_ONLY) { P.eps = CUDART_INF_F; P.eps_b = CUDART_INF_F; }
+        if ((p.flags & SATMC_EXACT_ONLY) || !src.robot_is_centred_rect()) { P.eps = CUDART_INF_F; P.eps_b = CUDART_INF_F; }
         __syncwarp();
-        if (lane == 0) { exact_robot_corners(v[0], v[1], P.ca, P.sa, v[3], v[4], s_robot[warp]); s_pair[warp] = P; }
+        if (lane == 0) {
+            float base[8];
+            src.robot_base8(v, base);
+            exact_robot_corners(v[0], v[1], P.ca, P.sa, base, s_robot[warp]);
+            s_pair[warp] = P;
+        }
         __syncwarp();
         const PairConst& Pc = s_pair[warp];
         const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
         const uint64_t c_len = (c_begin + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - c_begin);
         unsigned long long* ev = (p.flags & SATMC_EXACT_ONLY) ? nullptr : p.exact_evals;
+        SATMC_ASSERT(pair < p.hits_len && c_begin < p.n_samples);
         unsigned cnt;
         if (STREAMED) {
             const float* z = p.z + pair * p.z_pair_stride + c_begin;
             cnt = (p.ndof == 5) ? streamed_chunk<5>(P, Pc, s_robot[warp], z, p.ldz, c_len, p.vec_ok, lane, ev)
                                 : streamed_chunk<3>(P, Pc, s_robot[warp], z, p.ldz, c_len, p.vec_ok, lane, ev);
         } else {
-            const uint32_t pid = p.pair_id_offset + (uint32_t)elem;
+            const uint32_t pid = p.pair_id_offset + (uint32_t)elem * p.pair_id_stride;
             const uint64_t s_begin = p.sample_offset + c_begin;
             const bool dof3 = (v[10] == 0.0f) && (v[11] == 0.0f);
             cnt = dof3 ? fused_chunk<3, DEFER>(P, Pc, s_robot[warp], s_begin, s_begin + c_len, pid, p.keys, lane, ev, Q, (unsigned)pair)
@@ -392,14 +451,14 @@ __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED
                 unsigned long long t = 0;
 #pragma unroll
                 for (int w = 0; w < kWarps; w++) t += s_part[w];
-                atomicAdd(p.hits + pair, t);                       // one atomic per block
+                atomicAdd(counter_base(p) + pair, t);              // one atomic per block
             }
             __syncthreads();
         } else if (lane == 0) {
             if (p.n_chunks == 1) {
                 if (p.flags & SATMC_ACCUMULATE) p.hits[pair] += cnt; else p.hits[pair] = cnt;
             } else {
-                atomicAdd(p.hits + pair, (unsigned long long)cnt);
+                atomicAdd(counter_base(p) + pair, (unsigned long long)cnt);
             }
         }
         if (DEFER && Q != nullptr) {
@@ -409,6 +468,7 @@ __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED
         item = next_item(p, item, stride, drawn);
     }
     if (DEFER && Q != nullptr) cold_flush(Q, src, p, lane);
+    finalize_counters(p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -478,12 +538,18 @@ k_count_streamed_tma(const __grid_constant__ DirectSrc src, const __grid_constan
         pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
         if (p.flags & SATMC_EXACT_ONLY) { P.eps = CUDART_INF_F; P.eps_b = CUDART_INF_F; }
         __syncwarp();
-        if (lane == 0) { exact_robot_corners(v[0], v[1], P.ca, P.sa, v[3], v[4], s_robot[warp]); s_pair[warp] = P; }
+        if (lane == 0) {
+            float base[8];
+            src.robot_base8(v, base);
+            exact_robot_corners(v[0], v[1], P.ca, P.sa, base, s_robot[warp]);
+            s_pair[warp] = P;
+        }
         __syncwarp();
         const PairConst& Pc = s_pair[warp];
         const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
         const uint64_t c_len = (c_begin + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - c_begin);
         unsigned long long* ev = (p.flags & SATMC_EXACT_ONLY) ? nullptr : p.exact_evals;
+        SATMC_ASSERT(pair < p.hits_len && c_begin < p.n_samples);
         const float* z = p.z + pair * p.z_pair_stride + c_begin;
         const uint32_t n_tiles = (uint32_t)(c_len / kTile);
         const int x0 = (int)(pair * p.z_pair_stride + c_begin);       // tensor coordinate of the chunk (< 2^31, host-checked)
@@ -528,18 +594,19 @@ k_count_streamed_tma(const __grid_constant__ DirectSrc src, const __grid_constan
                 unsigned long long tsum = 0;
 #pragma unroll
                 for (int w = 0; w < kWarps; w++) tsum += s_part[w];
-                atomicAdd(p.hits + pair, tsum);
+                atomicAdd(counter_base(p) + pair, tsum);
             }
             __syncthreads();
         } else if (lane == 0) {
             if (p.n_chunks == 1) {
                 if (p.flags & SATMC_ACCUMULATE) p.hits[pair] += cnt; else p.hits[pair] = cnt;
             } else {
-                atomicAdd(p.hits + pair, (unsigned long long)cnt);
+                atomicAdd(counter_base(p) + pair, (unsigned long long)cnt);
             }
         }
         item = next_item(p, item, stride, drawn);
     }
+    finalize_counters(p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -698,12 +765,17 @@ __global__ void __launch_bounds__(32 * sweep_warps(SHARE), 2) k_count_sweep(cons
             S.sig[c][0] = sx; S.sig[c][1] = sy; S.sig[c][2] = st;
             S.cnt[c] = 0;
         }
-        if (lane == 0) { exact_robot_corners(v[0], v[1], P.ca, P.sa, v[3], v[4], S.robot); S.base = P; }
+        if (lane == 0) {
+            float base[8];
+            rect_base(v[3], v[4], base);
+            exact_robot_corners(v[0], v[1], P.ca, P.sa, base, S.robot);
+            S.base = P;
+        }
         __syncwarp();
         const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
         const uint64_t c_len = (c_begin + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - c_begin);
         unsigned long long* ev = (p.flags & SATMC_EXACT_ONLY) ? nullptr : p.exact_evals;
-        const uint32_t pid = p.pair_id_offset + (uint32_t)pair;
+        const uint32_t pid = p.pair_id_offset + (uint32_t)pair * p.pair_id_stride;
         const uint64_t b = p.sample_offset + c_begin, e = b + c_len;
         const uint64_t q_lo = (b + 7) >> 3, q_hi = e >> 3;              // full 8-sample super-groups [q_lo, q_hi)
         if (SHARE && q_lo <= q_hi) {
@@ -758,12 +830,17 @@ __global__ void __launch_bounds__(32 * sweep_warps(SHARE), 2) k_count_sweep(cons
         __syncwarp();
         for (int c = lane; c < n_cov; c += 32) {
             const unsigned long long tot = S.cnt[c];
-            unsigned long long* dst = p.hits + pair * hits_stride + c;
-            if (p.n_chunks == 1) { if (p.flags & SATMC_ACCUMULATE) *dst += tot; else *dst = tot; }
-            else atomicAdd(dst, tot);
+            SATMC_ASSERT(pair * hits_stride + c < p.hits_len);
+            if (p.n_chunks == 1) {
+                unsigned long long* dst = p.hits + pair * hits_stride + c;
+                if (p.flags & SATMC_ACCUMULATE) *dst += tot; else *dst = tot;
+            } else {
+                atomicAdd(counter_base(p) + pair * hits_stride + c, tot);
+            }
         }
         __syncwarp();
     }
+    finalize_counters(p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -830,7 +907,7 @@ __device__ __forceinline__ unsigned poly_chunk(const PolyPairShared& S, const Po
             if (fill >= 32u) cnt += poly_queue_drain<NR, NO>(S, R, Q, fill, false, lane, ev);
         }
     } else {
-        const uint32_t pid = p.pair_id_offset + (uint32_t)pair;
+        const uint32_t pid = p.pair_id_offset + (uint32_t)pair * p.pair_id_stride;
         const uint64_t b = p.sample_offset + c_begin, e = b + c_len;
         const uint64_t g_end = (e + 3) >> 2;
         for (uint64_t g0 = b >> 2; g0 < g_end; g0 += 32) {               // 4-sample groups, ragged ends masked
@@ -861,6 +938,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_count_poly(const float* __restr
         const unsigned long long drawn = draw_ticket(p, lane);
         const uint64_t pair = item / p.n_chunks;
         const uint32_t chunk_id = (uint32_t)(item - pair * p.n_chunks);
+        SATMC_ASSERT(pair < p.hits_len);
         __syncwarp();
         if (lane == 0) {
             poly_prologue(s_poly[warp], pairs + pair * 40);                        // 160-byte descriptors
@@ -887,18 +965,19 @@ __global__ void __launch_bounds__(kThreads, 2) k_count_poly(const float* __restr
                 unsigned long long t = 0;
 #pragma unroll
                 for (int w = 0; w < kWarps; w++) t += s_part[w];
-                atomicAdd(p.hits + pair, t);
+                atomicAdd(counter_base(p) + pair, t);
             }
             __syncthreads();
         } else if (lane == 0) {
             if (p.n_chunks == 1) {
                 if (p.flags & SATMC_ACCUMULATE) p.hits[pair] += cnt; else p.hits[pair] = cnt;
             } else {
-                atomicAdd(p.hits + pair, (unsigned long long)cnt);
+                atomicAdd(counter_base(p) + pair, (unsigned long long)cnt);
             }
         }
         item = next_item(p, item, stride, drawn);
     }
+    finalize_counters(p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -914,7 +993,11 @@ __global__ void k_decide(satmc_pair const* pair, const float* __restrict__ z, ui
     PairConst P;
     pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
     if (flags & SATMC_EXACT_ONLY) { P.eps = CUDART_INF_F; P.eps_b = CUDART_INF_F; }
-    if (threadIdx.x == 0) exact_robot_corners(v[0], v[1], P.ca, P.sa, v[3], v[4], s_robot);
+    if (threadIdx.x == 0) {
+        float base[8];
+        rect_base(v[3], v[4], base);
+        exact_robot_corners(v[0], v[1], P.ca, P.sa, base, s_robot);
+    }
     __syncthreads();
     unsigned long long* ev = (flags & SATMC_EXACT_ONLY) ? nullptr : exact_evals;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -1022,21 +1105,34 @@ __global__ void k_iota(int* a, int n)
     if (i < n) a[i] = i;
 }
 
-// Splits the live list: finished pairs get their probability written in place (count / n_samples, the
-// arithmetic of write_collision_probability utils.cu:210-215) and leave the list, the rest are appended
-// to live_out.  Warp-aggregated append: one atomic per warp.
-__global__ void k_compact_live(const int* __restrict__ live_in, int num_left, const int* __restrict__ done,
-                               const float* __restrict__ counts, int n_samples, float* cp_out, int* n_samples_out,
-                               int* live_out, int* n_out, int finalize_all)
+// Tail of one adaptive iteration in one kernel: the reference kernel's z-test tail (ztest.cu:156-165) for the pair of
+// every live slot, then the split of the live list: a finished pair gets its probability written in input order
+// (count / n_samples, the arithmetic of write_collision_probability utils.cu:210-215) and leaves the list, the others
+// are appended to live_out -- warp-aggregated, one atomic per warp (the reference: thrust::count + sort_by_key + 4-5
+// blocking copies, ztest.cu:359-371).  n_out must be zero on entry; n_next (the other of the two counters, used by
+// the next iteration) is cleared here, so the loop needs no memset.
+__global__ void k_ztest_compact(const unsigned long long* __restrict__ hits, float* counts, const float* __restrict__ bins,
+                                const float* __restrict__ bin_acc, int n_bins, int n_samples, int num_left,
+                                const int* __restrict__ live_in, float* cp_out, int* n_samples_out, int* live_out, int* n_out,
+                                int* n_next, int n_pairs)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *n_next = 0;
     const bool valid = i < num_left;
     int e = 0; bool keep = false;
     if (valid) {
         e = live_in[i];
-        const bool fin = finalize_all || done[e] != 0;
+        SATMC_ASSERT(e >= 0 && e < n_pairs);
+        const int k = (int)counts[e] + (int)hits[i];
+        const float slack = calc_slack(n_samples, k);
+        const float p = (float)k / (float)n_samples;
+        int bin = 0;
+        for (int b = 0; b + 1 < n_bins; b++)
+            if (p >= bins[b] && p <= bins[b + 1]) bin = b;
+        const bool fin = slack <= bin_acc[bin];
+        counts[e] = (float)k;
         if (fin) {
-            cp_out[e] = counts[e] / (float)n_samples;
+            cp_out[e] = (float)k / (float)n_samples;
             if (n_samples_out) n_samples_out[e] = n_samples;
         }
         keep = !fin;
@@ -1047,7 +1143,23 @@ __global__ void k_compact_live(const int* __restrict__ live_in, int num_left, co
     int base = 0;
     if (lane == __ffs(m) - 1) base = atomicAdd(n_out, __popc(m));
     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (keep) live_out[base + __popc(m & ((1u << lane) - 1u))] = e;
+    if (keep) {
+        const int pos = base + __popc(m & ((1u << lane) - 1u));
+        SATMC_ASSERT(pos >= 0 && pos < num_left);
+        live_out[pos] = e;
+    }
+}
+
+// pairs still live when the loop stops at max_samples: probability from the counts as they stand (ztest.cu:376-385)
+__global__ void k_compact_live(const int* __restrict__ live_in, int num_left, const float* __restrict__ counts, int n_samples,
+                               float* cp_out, int* n_samples_out, int n_pairs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_left) return;
+    const int e = live_in[i];
+    SATMC_ASSERT(e >= 0 && e < n_pairs);
+    cp_out[e] = counts[e] / (float)n_samples;
+    if (n_samples_out) n_samples_out[e] = n_samples;
 }
 
 // iteration-0 draw of generate_dataset (generate_dataset.cu:207-219): pose index, std-dev index and a

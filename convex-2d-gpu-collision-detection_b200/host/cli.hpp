@@ -6,6 +6,8 @@
 //   bool values 1/0/true/false/on/off/yes/no; switches take no value
 //   unknown / ambiguous option or missing value -> std::runtime_error (boost throws, the reference aborts)
 #pragma once
+#include <cerrno>
+#include <climits>
 #include <cstdlib>
 #include <iostream>
 #include <map>
@@ -74,9 +76,23 @@ public:
     int integer(const std::string& name) const {
         const std::string v = str(name);
         char* end = nullptr;
-        long x = std::strtol(v.c_str(), &end, 10);
-        if (end == v.c_str() || *end) throw std::runtime_error("the argument ('" + v + "') for option '--" + name + "' is invalid");
+        errno = 0;
+        long long x = std::strtoll(v.c_str(), &end, 10);
+        if (end == v.c_str() || *end || errno == ERANGE || x < INT_MIN || x > INT_MAX)      // boost: bad_lexical_cast
+            throw std::runtime_error("the argument ('" + v + "') for option '--" + name + "' is invalid");
         return (int)x;
+    }
+    // unsigned 64-bit value (--seed): the whole range is accepted, anything else is rejected rather than truncated
+    unsigned long long unsigned64(const std::string& name) const {
+        const std::string v = str(name);
+        char* end = nullptr;
+        errno = 0;
+        if (v.empty() || v[0] == '-' || v[0] == '+' || v[0] == ' ')
+            throw std::runtime_error("the argument ('" + v + "') for option '--" + name + "' is invalid");
+        unsigned long long x = std::strtoull(v.c_str(), &end, 10);
+        if (end == v.c_str() || *end || errno == ERANGE)
+            throw std::runtime_error("the argument ('" + v + "') for option '--" + name + "' is invalid");
+        return x;
     }
     float real(const std::string& name) const { return to_float(str(name), name); }
     bool boolean(const std::string& name) const {

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <ctime>
 #include <filesystem>
+#include <future>
 #include <iostream>
 #include <random>
 
@@ -28,7 +29,8 @@ struct Arguments {
     int max_samples = 4000000;
     float robot_width = 4.07f, robot_height = 1.74f;
     bool shuffle = true;
-    long long seed = -1;
+    uint64_t seed = 0;
+    bool has_seed = false, stats = false;
     int device = 0, gpus = 1;
 };
 
@@ -43,7 +45,8 @@ static Arguments parse_args(int argc, char** argv) {
      .add("robot_width", Kind::Float, "robot width", 'w')
      .add("robot_height", Kind::Float, "robot height", 'h')
      .add("shuffle", Kind::Bool, "whether or not to shuffle data")
-     .add("seed", Kind::Int, "RNG seed (default: 1804289383, glibc's first rand(), as upstream)")
+     .add("seed", Kind::String, "RNG seed (default: 1804289383, glibc's first rand(), as upstream)")
+     .add("stats", Kind::Switch, "print a one-line timing summary at the end")
      .add("device", Kind::Int, "CUDA device index (first device when --gpus > 1)")
      .add("gpus", Kind::Int, "number of GPUs to shard the rows of each file over");
     p.parse(argc, argv);
@@ -54,7 +57,8 @@ static Arguments parse_args(int argc, char** argv) {
     if (p.count("robot_width")) a.robot_width = p.real("robot_width");
     if (p.count("robot_height")) a.robot_height = p.real("robot_height");
     if (p.count("shuffle")) a.shuffle = p.boolean("shuffle");
-    if (p.count("seed")) a.seed = p.integer("seed");
+    if (p.count("seed")) { a.seed = p.unsigned64("seed"); a.has_seed = true; }
+    if (p.count("stats")) a.stats = true;
     if (p.count("device")) a.device = p.integer("device");
     if (p.count("gpus")) a.gpus = p.integer("gpus");
     return a;
@@ -93,33 +97,64 @@ int main(int argc, char* argv[]) try {
 
     ShardedMonteCarlo mc(args.device, args.gpus, args.robot_width, args.robot_height, poses, to_std_devs(variances), accuracy_bins,
                          bin_accuracy);
-    const uint64_t seed = args.seed >= 0 ? (uint64_t)args.seed : 1804289383ull;
+    const uint64_t seed = args.has_seed ? args.seed : 1804289383ull;
     auto begin = std::chrono::steady_clock::now();
     std::cout << "Begin computation..." << std::endl;
     int counter = 0;
     printf("batches generated: %i/%i\n", counter, num_batches);
-    uint64_t stream = 0;
-    for (int b = 0; b < num_batches; b++) {
-        std::vector<PositionWithVarAndPoseIdx> rows = load_rows<PositionWithVarAndPoseIdx>(data_in + "/" + std::to_string(b) + ".npy", 4);
-        const int n = (int)rows.size();
-        if (b == 0) std::cout << "num data points: " << n << std::endl;
-        std::vector<float> pos(2 * (size_t)n), var_idx(n), pose_idx(n);
-        for (int i = 0; i < n; i++) {                                                 // :262-268
-            pos[2 * i] = rows[i].x; pos[2 * i + 1] = rows[i].y; var_idx[i] = rows[i].var_idx; pose_idx[i] = rows[i].pose_idx;
+    // Three stages in flight: file b+1 is read and unpacked, and file b-1 assembled, shuffled and written, by helper
+    // threads while the GPUs run the adaptive loop of file b (upstream does the three in sequence, :259-360).
+    struct Input {
+        std::vector<PositionWithVarAndPoseIdx> rows;
+        std::vector<float> pos, var_idx, pose_idx;
+    };
+    auto load = [&](int b) {
+        Input in;
+        in.rows = load_rows<PositionWithVarAndPoseIdx>(data_in + "/" + std::to_string(b) + ".npy", 4);
+        const size_t n = in.rows.size();
+        in.pos.resize(2 * n); in.var_idx.resize(n); in.pose_idx.resize(n);
+        for (size_t i = 0; i < n; i++) {                                              // :262-268
+            in.pos[2 * i] = in.rows[i].x; in.pos[2 * i + 1] = in.rows[i].y;
+            in.var_idx[i] = in.rows[i].var_idx; in.pose_idx[i] = in.rows[i].pose_idx;
         }
-        std::vector<float> cp = mc.run_rows(pos, pose_idx, var_idx, Schedule::dataset(args.max_samples), seed,
-                                            (uint32_t)(stream & 0xffffffffu));
-        stream += (uint64_t)n;
+        return in;
+    };
+    auto store = [&](int b, std::vector<PositionWithVarAndPoseIdx> rows, std::vector<float> cp) {
+        const size_t n = rows.size();
         std::vector<PoseCPVarAndPoseIdx> dataset(n);
-        for (int j = 0; j < n; j++) dataset[j] = {rows[j].x, rows[j].y, cp[j], rows[j].var_idx, rows[j].pose_idx};   // :337-344
-        if (args.shuffle) std::shuffle(dataset.begin(), dataset.end(), std::default_random_engine(0));               // :346-349
-        npyio::save_f32(data_out + "/" + std::to_string(start_batch_count + b) + ".npy", {(size_t)n, 5},
+        for (size_t j = 0; j < n; j++) dataset[j] = {rows[j].x, rows[j].y, cp[j], rows[j].var_idx, rows[j].pose_idx};   // :337-344
+        if (args.shuffle) std::shuffle(dataset.begin(), dataset.end(), std::default_random_engine(0));                  // :346-349
+        npyio::save_f32(data_out + "/" + std::to_string(start_batch_count + b) + ".npy", {n, 5},
                         reinterpret_cast<const float*>(dataset.data()));
+    };
+    StreamCursor cursor;                                 // 64-bit running row index: 32-bit stream id + epoch in the seed
+    double gpu_s = 0;
+    std::future<Input> next;
+    std::future<void> pending_write;
+    if (num_batches > 0) next = std::async(std::launch::async, load, 0);
+    for (int b = 0; b < num_batches; b++) {
+        Input in = next.get();
+        if (b + 1 < num_batches) next = std::async(std::launch::async, load, b + 1);
+        const int n = (int)in.rows.size();
+        if (b == 0) std::cout << "num data points: " << n << std::endl;
+        const uint32_t first_stream = cursor.take((uint64_t)n);
+        const auto t_gpu = std::chrono::steady_clock::now();
+        std::vector<float> cp = mc.run_rows(in.pos, in.pose_idx, in.var_idx, Schedule::dataset(args.max_samples), cursor.seed(seed),
+                                            first_stream);
+        gpu_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_gpu).count();
+        if (pending_write.valid()) pending_write.get();                                // at most one file behind
+        pending_write = std::async(std::launch::async, store, b, std::move(in.rows), std::move(cp));
         auto end = std::chrono::steady_clock::now();
         printf("\33[2K\r");
         printf("batches generated: %i/%i, Time: %i [min]", ++counter, num_batches,
                (int)std::chrono::duration_cast<std::chrono::minutes>(end - begin).count());
         fflush(stdout);
+    }
+    if (pending_write.valid()) pending_write.get();
+    if (args.stats) {
+        const double total = std::chrono::duration<double>(std::chrono::steady_clock::now() - begin).count();
+        printf("\nstats: {\"files\": %d, \"total_s\": %.3f, \"gpu_loop_busy_s\": %.3f, \"gpu_busy_frac\": %.3f, \"gpus\": %d}", num_batches,
+               total, gpu_s, total > 0 ? gpu_s / total : 0.0, args.gpus);
     }
     std::cout << std::endl;
     auto end = std::chrono::steady_clock::now();

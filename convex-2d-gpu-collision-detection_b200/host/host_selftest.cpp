@@ -2,11 +2,15 @@
 //   host_selftest npy-write <file> <rows> <cols>     writes a[i][j] = i + j/16
 //   host_selftest npy-read <file>                     prints shape and a checksum
 //   host_selftest cli <args...>                       parses generate_dataset-style flags, prints what it saw
+//   host_selftest tables <n_variances> <n_poses>      parallel table generation == the sequential std:: loop
+//   host_selftest seed <text>                         64-bit --seed parsing
 #include <cstdio>
+#include <cstring>
 #include <iostream>
 
 #include "cli.hpp"
 #include "npy.hpp"
+#include "tables.hpp"
 
 int main(int argc, char** argv) try {
     if (argc < 2) return 64;
@@ -25,6 +29,33 @@ int main(int argc, char** argv) try {
         std::printf("ndim %zu shape", a.shape.size());
         for (size_t s : a.shape) std::printf(" %zu", s);
         std::printf(" sum %.6f first %.6f last %.6f\n", sum, a.data.empty() ? 0.0 : a.data.front(), a.data.empty() ? 0.0 : a.data.back());
+        return 0;
+    }
+    if (mode == "tables" && argc == 4) {
+        // parallel skip-ahead generation == upstream's sequential std:: loop, bit for bit (variances then poses)
+        const size_t nv = std::stoul(argv[2]), np_ = std::stoul(argv[3]);
+        const float vmin[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, vmax[5] = {.3f, .3f, .3f, 0.f, 0.f};
+        const float pmin[3] = {0.1f, 0.1f, 0.f}, pmax[3] = {5.f, 5.f, 6.2831855f};
+        std::vector<float> v_ref(5 * nv), p_ref(3 * np_), v(5 * nv), q(3 * np_);
+        std::default_random_engine gen;
+        tables::fill_uniform_rows_std(v_ref.data(), nv, 5, vmin, vmax, gen);
+        tables::fill_uniform_rows_std(p_ref.data(), np_, 3, pmin, pmax, gen);
+        size_t bad = 0;
+        for (unsigned threads : {1u, 3u, 8u}) {
+            tables::fill_uniform_rows(v.data(), nv, 5, vmin, vmax, 0, threads);
+            tables::fill_uniform_rows(q.data(), np_, 3, pmin, pmax, 5ull * nv, threads);
+            for (size_t i = 0; i < v.size(); i++) bad += std::memcmp(&v[i], &v_ref[i], 4) != 0;
+            for (size_t i = 0; i < q.size(); i++) bad += std::memcmp(&q[i], &p_ref[i], 4) != 0;
+        }
+        std::printf("mismatches %zu\n", bad);
+        return bad ? 3 : 0;
+    }
+    if (mode == "seed" && argc == 3) {
+        cli::Parser p("o");
+        p.add("seed", cli::Kind::String, "seed");
+        char* av[] = {argv[0], (char*)"--seed", argv[2]};
+        p.parse(3, av);
+        std::printf("%llu\n", p.unsigned64("seed"));
         return 0;
     }
     if (mode == "cli") {

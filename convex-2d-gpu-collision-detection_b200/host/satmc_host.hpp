@@ -57,6 +57,8 @@ public:
     size_t size() const { return n_; }
     void upload(const T* src, size_t n) { ctx_.check(satmc_upload(ctx_.get(), p_, src, n * sizeof(T)), "satmc_upload"); }
     void download(T* dst, size_t n) const { ctx_.check(satmc_download(ctx_.get(), dst, p_, n * sizeof(T)), "satmc_download"); }
+    // enqueue only (pinned destination); complete after satmc_synchronize
+    void download_async(T* dst, size_t n) const { ctx_.check(satmc_download_async(ctx_.get(), dst, p_, n * sizeof(T)), "satmc_download_async"); }
     std::vector<T> to_host() const { std::vector<T> v(n_); download(v.data(), n_); return v; }
 private:
     Context& ctx_;
@@ -67,10 +69,18 @@ private:
 // std_dev = sqrt(variance), component-wise (generate_dataset.cu:309-317, ztest.cu:245-251)
 inline std::vector<StdDev> to_std_devs(const std::vector<Variance>& v) {
     std::vector<StdDev> s(v.size());
-    for (size_t i = 0; i < v.size(); i++) {
-        s[i].x = std::sqrt(v[i].x); s[i].y = std::sqrt(v[i].y); s[i].theta = std::sqrt(v[i].theta);
-        s[i].width = std::sqrt(v[i].width); s[i].height = std::sqrt(v[i].height);
-    }
+    auto work = [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            s[i].x = std::sqrt(v[i].x); s[i].y = std::sqrt(v[i].y); s[i].theta = std::sqrt(v[i].theta);
+            s[i].width = std::sqrt(v[i].width); s[i].height = std::sqrt(v[i].height);
+        }
+    };
+    unsigned threads = v.size() >= (1u << 16) ? std::thread::hardware_concurrency() : 1;
+    if (threads == 0) threads = 1;
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < threads; t++) pool.emplace_back(work, v.size() * t / threads, v.size() * (t + 1) / threads);
+    work(0, v.size() / threads);
+    for (std::thread& t : pool) t.join();
     return s;
 }
 
@@ -91,14 +101,11 @@ class MonteCarlo {
 public:
     MonteCarlo(Context& ctx, float robot_w, float robot_h, const std::vector<Pose>& poses, const std::vector<StdDev>& sds,
                const std::vector<float>& accuracy_bins, const std::vector<float>& bin_accuracy)
-        : ctx_(ctx), n_poses_((uint32_t)poses.size()), n_std_((uint32_t)sds.size()), n_bins_((int)accuracy_bins.size()),
+        : ctx_(validated(ctx, poses.size(), sds.size(), accuracy_bins.size(), bin_accuracy.size())),
+          n_poses_((uint32_t)poses.size()), n_std_((uint32_t)sds.size()), n_bins_((int)accuracy_bins.size()),
           d_robot_(ctx, create_rect(robot_w, robot_h)),
           d_poses_(ctx, flatten(poses)), d_sds_(ctx, flatten(sds)), d_bins_(ctx, accuracy_bins),
-          d_acc_(ctx, padded(bin_accuracy, accuracy_bins.size())) {
-        if (poses.empty() || sds.empty()) throw Error(SATMC_ERR_INVALID, "empty pose or variance table");
-        if (accuracy_bins.size() < 2 || bin_accuracy.size() + 1 < accuracy_bins.size())
-            throw Error(SATMC_ERR_INVALID, "need n accuracy_bins (n >= 2) and n-1 bin_accuracy values");
-    }
+          d_acc_(ctx, padded(bin_accuracy, accuracy_bins.size())) {}
 
     // generate_dataset iteration 0: draws (pose_idx, var_idx, position) for n data points
     void sample_positions(int n, float r_offset, float spread, uint64_t seed, uint32_t stream_offset,
@@ -118,6 +125,12 @@ public:
     }
 
 private:
+    // argument checks run before the first member allocates or uploads anything
+    static Context& validated(Context& ctx, size_t n_poses, size_t n_sds, size_t n_bins, size_t n_acc) {
+        if (n_poses == 0 || n_sds == 0) throw Error(SATMC_ERR_INVALID, "empty pose or variance table");
+        if (n_bins < 2 || n_acc + 1 < n_bins) throw Error(SATMC_ERR_INVALID, "need n accuracy_bins (n >= 2) and n-1 bin_accuracy values");
+        return ctx;
+    }
     template <class T> static std::vector<float> flatten(const std::vector<T>& v) {
         const float* p = reinterpret_cast<const float*>(v.data());
         return std::vector<float>(p, p + v.size() * (sizeof(T) / sizeof(float)));
@@ -130,67 +143,83 @@ private:
     DeviceArray<float> d_robot_, d_poses_, d_sds_, d_bins_, d_acc_;
 };
 
-// The tables resident on `gpus` devices starting at `first_device` (one context per GPU, created once) and the
-// adaptive z-test over n host-side rows sharded across them: one host thread per GPU, contiguous row ranges.  Row i
-// always draws Philox stream stream_offset + i, so cp[] does not depend on the number of GPUs.
+// Pinned host memory (satmc_host_alloc): download target of the double-buffered batch loop.
+template <class T>
+class PinnedArray {
+public:
+    explicit PinnedArray(size_t n) : n_(n) {
+        if (satmc_host_alloc(reinterpret_cast<void**>(&p_), n * sizeof(T)) != SATMC_OK)
+            throw Error(SATMC_ERR_NOMEM, std::string("satmc_host_alloc: ") + satmc_last_error(nullptr));
+    }
+    ~PinnedArray() { satmc_host_free(p_); }
+    PinnedArray(const PinnedArray&) = delete;
+    PinnedArray& operator=(const PinnedArray&) = delete;
+    T* get() const { return p_; }
+    size_t size() const { return n_; }
+    const T& operator[](size_t i) const { return p_[i]; }
+private:
+    T* p_ = nullptr;
+    size_t n_;
+};
+
+// The adaptive z-test over host rows on `gpus` devices starting at `first_device`, through the library's group entry
+// points (satmc_group_*): the tables are made resident on every device once, rows are dealt round-robin to the GPUs
+// (work per row varies ~400x, generate_dataset.cu:53,427-431), the devices advance in lockstep from this thread.
+// Row i always draws Philox stream stream_offset + i, so cp[] does not depend on the number of GPUs.
 class ShardedMonteCarlo {
 public:
     ShardedMonteCarlo(int first_device, int gpus, float robot_w, float robot_h, const std::vector<Pose>& poses,
                       const std::vector<StdDev>& sds, const std::vector<float>& accuracy_bins, const std::vector<float>& bin_accuracy) {
         if (gpus < 1) gpus = 1;
-        for (int w = 0; w < gpus; w++) {
-            ctx_.emplace_back(new Context(first_device + w));
-            mc_.emplace_back(new MonteCarlo(*ctx_.back(), robot_w, robot_h, poses, sds, accuracy_bins, bin_accuracy));
+        if (poses.empty() || sds.empty()) throw Error(SATMC_ERR_INVALID, "empty pose or variance table");
+        if (accuracy_bins.size() < 2 || bin_accuracy.size() + 1 < accuracy_bins.size())
+            throw Error(SATMC_ERR_INVALID, "need n accuracy_bins (n >= 2) and n-1 bin_accuracy values");
+        std::vector<int> devices;
+        for (int w = 0; w < gpus; w++) devices.push_back(first_device + w);
+        int rc = satmc_group_create(devices.data(), gpus, &g_);
+        if (rc != SATMC_OK) throw Error(rc, std::string("satmc_group_create: ") + satmc_group_last_error(nullptr));
+        const std::vector<float> robot = create_rect(robot_w, robot_h);
+        rc = satmc_group_set_tables(g_, robot.data(), reinterpret_cast<const float*>(poses.data()), (uint32_t)poses.size(),
+                                    reinterpret_cast<const float*>(sds.data()), (uint32_t)sds.size(), accuracy_bins.data(),
+                                    bin_accuracy.data(), (int)accuracy_bins.size());
+        if (rc != SATMC_OK) {
+            const std::string msg = std::string("satmc_group_set_tables: ") + satmc_group_last_error(g_);
+            satmc_group_destroy(g_);
+            throw Error(rc, msg);
         }
     }
-    ~ShardedMonteCarlo() {
-        for (MonteCarlo* m : mc_) delete m;
-        for (Context* c : ctx_) delete c;
-    }
+    ~ShardedMonteCarlo() { satmc_group_destroy(g_); }
     ShardedMonteCarlo(const ShardedMonteCarlo&) = delete;
     ShardedMonteCarlo& operator=(const ShardedMonteCarlo&) = delete;
 
     std::vector<float> run_rows(const std::vector<float>& pos, const std::vector<float>& pose_idx, const std::vector<float>& var_idx,
                                 const Schedule& schedule, uint64_t seed, uint32_t stream_offset, int* iterations = nullptr,
                                 long long* samples = nullptr) {
-        const size_t n = pose_idx.size();
-        const size_t gpus = ctx_.size();
-        std::vector<float> cp(n);
-        std::mutex m;
-        std::string failure;
-        int max_iter = 0; long long total = 0;
-        auto worker = [&](size_t w) {
-            try {
-                const size_t lo = n * w / gpus, hi = n * (w + 1) / gpus;
-                if (hi == lo) return;
-                Context& ctx = *ctx_[w];
-                const size_t k = hi - lo;
-                DeviceArray<float> d_pos(ctx, 2 * k), d_pi(ctx, k), d_vi(ctx, k), d_cp(ctx, k);
-                d_pos.upload(pos.data() + 2 * lo, 2 * k); d_pi.upload(pose_idx.data() + lo, k); d_vi.upload(var_idx.data() + lo, k);
-                int it = 0; long long smp = 0;
-                mc_[w]->run(d_pos, d_pi, d_vi, (int)k, schedule, seed, stream_offset + (uint32_t)lo, d_cp, &it, &smp);
-                d_cp.download(cp.data() + lo, k);
-                std::lock_guard<std::mutex> lock(m);
-                if (it > max_iter) max_iter = it;
-                total += smp;
-            } catch (const std::exception& e) {
-                std::lock_guard<std::mutex> lock(m);
-                if (failure.empty()) failure = std::string("GPU shard ") + std::to_string(w) + ": " + e.what();
-            }
-        };
-        std::vector<std::thread> threads;
-        for (size_t w = 1; w < gpus; w++) threads.emplace_back(worker, w);
-        worker(0);
-        for (std::thread& t : threads) t.join();
-        if (!failure.empty()) throw Error(SATMC_ERR_CUDA, failure);
-        if (iterations) *iterations = max_iter;
-        if (samples) *samples = total;
+        std::vector<float> cp(pose_idx.size());
+        const int rc = satmc_group_adaptive_run_host(g_, pose_idx.data(), var_idx.data(), pos.data(), (int)pose_idx.size(),
+                                                     schedule.max_samples, schedule.n_batch_small, schedule.switch_at,
+                                                     schedule.n_batch_large, seed, stream_offset, cp.data(), iterations, samples);
+        if (rc != SATMC_OK) throw Error(rc, std::string("satmc_group_adaptive_run_host: ") + satmc_group_last_error(g_));
         return cp;
     }
 
 private:
-    std::vector<Context*> ctx_;
-    std::vector<MonteCarlo*> mc_;
+    satmc_group* g_ = nullptr;
+};
+
+// Philox stream ids are 32 bits.  Programs that number their rows with a 64-bit running index fold the high part into
+// the seed ("epoch") instead of letting ids wrap: rows 2^32 apart would otherwise share a stream at the same sample
+// indices and produce perfectly correlated estimates.  A block of rows never straddles an epoch.
+struct StreamCursor {
+    uint64_t epoch = 0, offset = 0;
+    // reserves n consecutive ids; returns the first
+    uint32_t take(uint64_t n) {
+        if (offset + n > 0x100000000ull) { epoch++; offset = 0; }
+        const uint32_t first = (uint32_t)offset;
+        offset += n;
+        return first;
+    }
+    uint64_t seed(uint64_t base) const { return base ^ (epoch * 0x9E3779B97F4A7C15ull); }
 };
 
 }  // namespace satmc_host

@@ -25,7 +25,8 @@ struct Arguments {
     int max_samples = 4000000;
     float robot_width = 4.07f, robot_height = 1.74f;
     bool shuffle = true, cps_only = false;
-    long long seed = -1;
+    uint64_t seed = 0;
+    bool has_seed = false;
     int device = 0, gpus = 1;
 };
 
@@ -43,7 +44,7 @@ static Arguments parse_args(int argc, char** argv) {
      .add("shuffle", Kind::Bool, "whether or not to shuffle data")
      .add("cps_only", Kind::Bool, "whether or not to only compute collision probabilities")
      .add("meta_dir", Kind::String, "path to meta folder containing accuracy_bins.npy and bin_accuracy.npy")
-     .add("seed", Kind::Int, "RNG seed (default: from the clock, as upstream)")
+     .add("seed", Kind::String, "RNG seed (default: from the clock, as upstream)")
      .add("device", Kind::Int, "CUDA device index (first device when --gpus > 1)")
      .add("gpus", Kind::Int, "number of GPUs to shard the rows over");
     p.parse(argc, argv);
@@ -57,7 +58,7 @@ static Arguments parse_args(int argc, char** argv) {
     if (p.count("shuffle")) a.shuffle = p.boolean("shuffle");
     if (p.count("cps_only")) a.cps_only = p.boolean("cps_only");
     if (p.count("meta_dir")) a.meta_dir = p.str("meta_dir");
-    if (p.count("seed")) a.seed = p.integer("seed");
+    if (p.count("seed")) { a.seed = p.unsigned64("seed"); a.has_seed = true; }
     if (p.count("device")) a.device = p.integer("device");
     if (p.count("gpus")) a.gpus = p.integer("gpus");
     return a;
@@ -115,7 +116,7 @@ int main(int argc, char* argv[]) try {
     for (int i = 0; i < n; i++) {                                                     // ztest.cu:262-268
         pos[2 * i] = rows[i].x; pos[2 * i + 1] = rows[i].y; var_idx[i] = rows[i].var_idx; pose_idx[i] = rows[i].pose_idx;
     }
-    const uint64_t seed = args.seed >= 0 ? (uint64_t)args.seed : (uint64_t)std::time(nullptr);
+    const uint64_t seed = args.has_seed ? args.seed : (uint64_t)std::time(nullptr);
 
     auto begin = std::chrono::steady_clock::now();
     std::cout << "Total number of configurations: " << n << std::endl;

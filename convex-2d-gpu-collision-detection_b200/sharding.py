@@ -2,6 +2,10 @@
 
 The path has no data dependence between units, so it shards two ways:
 
+The split itself lives behind the C ABI (``satmc_group_*`` in include/satmc.h: NCCL all-reduce / all-gather inside
+the library); this module restates its slice arithmetic for the CPU tests (gloo, world size 2) and offers the same
+two decompositions over any collective callable.
+
 * by pair (BASELINE cfg 3 / 5): rank r owns a contiguous slice of the pair array; Philox stream ids stay
   global through ``pair_id_offset``; no data-path collective (results are gathered only if the caller asks).
 * by sample range (cfg 4): rank r owns sample indices [lo_r, hi_r) of every pair (``sample_offset``); one
@@ -18,21 +22,25 @@ import numpy as np
 
 
 def pair_slice(n_pairs: int, rank: int, world: int) -> Tuple[int, int]:
-    """Contiguous slice [lo, hi) of the pair range owned by `rank` (sizes differ by at most one)."""
-    base, rem = divmod(n_pairs, world)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+    """Slice [lo, hi) of the pair range owned by `rank`: equal chunks of ceil(n / world) -- the layout of the in-place
+    all-gather inside ``satmc_group_count_fused`` (``satmc_shard_range(SATMC_SHARD_BY_PAIR)``, same arithmetic)."""
+    chunk = -(-n_pairs // world)
+    return min(rank * chunk, n_pairs), min((rank + 1) * chunk, n_pairs)
 
 
 def sample_slice(n_samples: int, rank: int, world: int, align: int = 4) -> Tuple[int, int]:
-    """Slice [lo, hi) of the sample range owned by `rank`, cut at multiples of `align`."""
+    """Slice [lo, hi) of the sample range owned by `rank`, cut at multiples of `align` (the sampler's group size);
+    ``satmc_shard_range(SATMC_SHARD_BY_SAMPLE_RANGE)``."""
     blocks = (n_samples + align - 1) // align
-    lo_b, hi_b = pair_slice(blocks, rank, world)
+    base, rem = divmod(blocks, world)
+    lo_b = rank * base + min(rank, rem)
+    hi_b = lo_b + base + (1 if rank < rem else 0)
     return min(lo_b * align, n_samples), min(hi_b * align, n_samples)
 
 
 def interleaved_indices(n_pairs: int, rank: int, world: int) -> np.ndarray:
-    """Round-robin assignment for adaptive (z-test) workloads, where work per pair varies ~400x."""
+    """Round-robin assignment for adaptive (z-test) workloads, where work per pair varies ~400x
+    (``satmc_shard_range(SATMC_SHARD_INTERLEAVED)``; what ``satmc_group_adaptive_run_host`` does)."""
     return np.arange(rank, n_pairs, world)
 
 

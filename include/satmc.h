@@ -36,14 +36,15 @@ extern "C" {
 #endif
 
 #define SATMC_VERSION_MAJOR 0
-#define SATMC_VERSION_MINOR 1
+#define SATMC_VERSION_MINOR 2
 
 typedef enum {
     SATMC_OK              =  0,
     SATMC_ERR_INVALID     = -1,   /* bad argument (null pointer, ndof not 3/5, misaligned ...)      */
     SATMC_ERR_NO_DEVICE   = -2,   /* no CUDA device / not compute capability 10.x                    */
     SATMC_ERR_CUDA        = -3,   /* a CUDA runtime call failed; see satmc_last_error()              */
-    SATMC_ERR_NOMEM       = -4    /* host or device allocation failed                                */
+    SATMC_ERR_NOMEM       = -4,   /* host or device allocation failed                                */
+    SATMC_ERR_NCCL        = -5    /* NCCL is unavailable (libnccl.so.2 not loadable) or an NCCL call failed    */
 } satmc_status;
 
 /* One (robot, uncertain obstacle) pair in direct form: 12 packed float32 = 48 bytes.
@@ -102,12 +103,13 @@ int satmc_count_fused(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pair
                       uint32_t pair_id_offset, uint64_t* d_hits, uint32_t flags);
 
 /* Covariance sweep with common random numbers (the ztest-style variance sweep, BASELINE config 5): every pair is
- * evaluated under n_cov pose-covariance settings d_sigmas[c] = (sd_x, sd_y, sd_theta) on the same normals (64 settings
- * per kernel launch).
+ * evaluated under n_cov pose-covariance settings h_sigmas[c] = (sd_x, sd_y, sd_theta) on the same normals (64 settings
+ * per kernel launch).  The settings are a HOST array (3 * n_cov floats, read before the call returns): they travel to
+ * the kernels as launch parameters.
  * d_hits[i*n_cov + c] equals what satmc_count_fused returns for pair i with sd_* = d_sigmas[c], sd_w = sd_h = 0 and
  * the same (seed, pair id, sample range) -- bit for bit -- but the sampler runs once per sample instead of once
  * per (sample, setting).  The sd_* fields of d_pairs are ignored. */
-int satmc_count_fused_sweep(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pairs, const float* d_sigmas,
+int satmc_count_fused_sweep(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pairs, const float* h_sigmas,
                             uint32_t n_cov, uint64_t n_samples, uint64_t seed, uint64_t sample_offset,
                             uint32_t pair_id_offset, uint64_t* d_hits, uint32_t flags);
 
@@ -149,6 +151,10 @@ int satmc_screen_debug(satmc_ctx* ctx, const satmc_pair* d_pair, const float* d_
 /* Diagnostics: number of samples that the screening pass could not decide and that were re-evaluated
  * with the exact arithmetic, accumulated over all counting calls since the last reset. */
 int satmc_exact_evals(satmc_ctx* ctx, uint64_t* out, int reset);
+
+/* Diagnostics: how a call would be cut into work items (kind 0 = fused rectangles, 1 = streamed, 2 = polygons, 3 = sweep):
+ * samples per item and items per pair.  An item's hits are summed in 32 bits, so no item exceeds 2^31 samples. */
+int satmc_plan_debug(satmc_ctx* ctx, int kind, uint64_t n_pairs, uint64_t n_samples, uint64_t* chunk_out, uint64_t* n_chunks_out);
 
 /* ---- general convex polygons ---------------------------------------------------------------- */
 
@@ -236,6 +242,78 @@ int satmc_device_alloc(satmc_ctx* ctx, void** out, size_t bytes);
 int satmc_device_free(satmc_ctx* ctx, void* p);
 int satmc_upload(satmc_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 int satmc_download(satmc_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+/* Enqueues the copy and returns; h_dst should be pinned (satmc_host_alloc) and is valid after satmc_synchronize. */
+int satmc_download_async(satmc_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+
+/* ---- groups: the multi-GPU split of the path ------------------------------------------------------ */
+
+/* The reference is single-GPU (no cudaSetDevice, streams or collectives anywhere; a single pair with N = 1e11 is
+ * impossible there: `int n_samples`, float counter, ztest.cu:331,135,165).  The path shards with no data dependence
+ * (SURVEY.md section 8e), and because the normals of sample s of pair p depend only on (seed, p, s) every split returns
+ * the single-GPU counts bit for bit:
+ *   SATMC_SHARD_BY_PAIR          rank r owns pairs [r*c, (r+1)*c), c = ceil(n_pairs / world); outputs are disjoint, the
+ *                                only exchange is an all-gather of the counters (none inside a single process)
+ *   SATMC_SHARD_BY_SAMPLE_RANGE  rank r owns a range of the sample indices of every pair (cut at multiples of 4); ONE
+ *                                ncclAllReduce(ncclUint64, ncclSum) of the n_pairs counters over NVLink is the exchange
+ *   SATMC_SHARD_INTERLEAVED      rows r, r + world, ...: the adaptive z-test, whose work per row varies ~400x
+ *                                (generate_dataset.cu:53,427-431)
+ * A group is either one process driving n devices (satmc_group_create: ncclCommInitAll, one context and stream per
+ * device, launches enqueued from the calling thread) or one process per GPU (satmc_group_create_rank: rank 0 calls
+ * satmc_group_unique_id, the launcher distributes the 128 bytes, every rank joins with ncclCommInitRank).  NCCL is bound
+ * at run time (dlopen of libnccl.so.2); a group of world size 1 needs none. */
+#define SATMC_SHARD_BY_PAIR          0
+#define SATMC_SHARD_BY_SAMPLE_RANGE  1
+#define SATMC_SHARD_INTERLEAVED      2
+#define SATMC_UNIQUE_ID_BYTES        128
+
+typedef struct satmc_group satmc_group;
+
+/* Slice of `rank` (host arithmetic only, no GPU needed).  BY_PAIR / BY_SAMPLE_RANGE: units [*lo, *hi).
+ * INTERLEAVED: *lo = first row, *hi = number of rows (rows *lo, *lo + world, ...). */
+int satmc_shard_range(int shard_mode, uint64_t n_units, int world, int rank, uint64_t* lo, uint64_t* hi);
+
+int satmc_group_create(const int* devices /* NULL = 0..n_dev-1 */, int n_dev, satmc_group** out);
+int satmc_group_unique_id(void* out /* SATMC_UNIQUE_ID_BYTES */);
+int satmc_group_create_rank(const void* unique_id, int world, int rank, int device, void* stream, satmc_group** out);
+int satmc_group_destroy(satmc_group* g);
+int satmc_group_synchronize(satmc_group* g);
+int satmc_group_world(const satmc_group* g);
+int satmc_group_local_count(const satmc_group* g);          /* devices driven by this process */
+int satmc_group_rank(const satmc_group* g, int local);      /* rank of local device `local` */
+satmc_ctx* satmc_group_context(satmc_group* g, int local);  /* its context (owned by the group) */
+const char* satmc_group_last_error(const satmc_group* g);
+int satmc_group_nccl_version(void);                         /* 0 if NCCL cannot be loaded */
+
+/* Counters a d_hits array must hold for n_pairs pairs: world * ceil(n_pairs / world) (the in-place all-gather layout). */
+uint64_t satmc_group_hits_capacity(const satmc_group* g, uint64_t n_pairs);
+
+/* satmc_count_fused over the group, inputs resident: d_pairs[l] = the FULL pair array on local device l, d_hits[l] =
+ * satmc_group_hits_capacity() counters there.  Every rank launches its shard and joins the collective on its stream;
+ * afterwards every d_hits[l][0..n_pairs) holds the counts of all pairs -- identical to satmc_count_fused on one GPU.
+ * Asynchronous (satmc_group_synchronize, or stream order on the streams given to satmc_group_create_rank). */
+int satmc_group_count_fused(satmc_group* g, const satmc_pair* const* d_pairs, uint64_t n_pairs, uint64_t n_samples,
+                            uint64_t seed, uint64_t sample_offset, uint32_t pair_id_offset, int shard_mode,
+                            uint64_t* const* d_hits, uint32_t flags);
+/* Same from host memory: every rank passes the same h_pairs, h_hits receives all n_pairs counts.  Blocking. */
+int satmc_group_count_fused_host(satmc_group* g, const satmc_pair* h_pairs, uint64_t n_pairs, uint64_t n_samples,
+                                 uint64_t seed, uint64_t sample_offset, uint32_t pair_id_offset, int shard_mode,
+                                 uint64_t* h_hits, uint32_t flags);
+/* With timing enabled satmc_group_count_fused brackets local device 0's kernel and the collective with CUDA events
+ * (and waits for them): the split of a step into compute and exchange that bench.py reports (allreduce_us). */
+int satmc_group_set_timing(satmc_group* g, int enabled);
+int satmc_group_last_times(const satmc_group* g, float* kernel_ms, float* collective_ms);
+
+/* The adaptive z-test loop (satmc_adaptive_run) over host rows dealt round-robin to the ranks.  The tables are made
+ * resident on every local device once (they are ~0.5 GB at the reference's defaults); row i always draws Philox stream
+ * stream_id_offset + i, so h_cp_out does not depend on the number of GPUs.
+ *   replaces: the per-file body of compute_collision_probability.cu:259-360 and ztest.cu:262-406 on n GPUs */
+int satmc_group_set_tables(satmc_group* g, const float* h_robot_base, const float* h_poses, uint32_t n_poses,
+                           const float* h_std_devs, uint32_t n_std, const float* h_accuracy_bins,
+                           const float* h_bin_accuracy, int n_accuracy_bins);
+int satmc_group_adaptive_run_host(satmc_group* g, const float* h_pose_idxs, const float* h_std_dev_idxs,
+                                  const float* h_positions, int n_rows, int max_samples, int n_batch_small, int switch_at,
+                                  int n_batch_large, uint64_t seed, uint32_t stream_id_offset, float* h_cp_out,
+                                  int* iterations_out, long long* samples_drawn_out);
 
 /* ---- host-buffer convenience (H2D + kernel + D2H inside the call) --------------------------- */
 

@@ -58,12 +58,31 @@ class Oracle:
         L.orc_fused_normals.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, fp]
         L.orc_count_fused_batch.argtypes = [fp, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, u64p, C.c_int]
         L.orc_hardware_threads.restype = C.c_int
+        L.orc_affinity_count.restype = C.c_int
+        L.orc_sat_batch_mt.argtypes = [fp, fp, C.c_size_t, u8p, C.c_int, C.c_int]
+        L.orc_count_streamed_mt.restype = C.c_uint64
+        L.orc_count_streamed_mt.argtypes = [fp, fp, C.c_size_t, C.c_int, C.c_size_t, C.c_int]
 
     # scalar helpers ---------------------------------------------------------------------------
     def cuda_sinf(self, x): return float(self.lib.orc_cuda_sinf(float(x)))
     def cuda_cosf(self, x): return float(self.lib.orc_cuda_cosf(float(x)))
     def calc_slack(self, n, k): return float(self.lib.orc_calc_slack(int(n), int(k)))
     def hardware_threads(self): return int(self.lib.orc_hardware_threads())
+    def affinity_count(self): return int(self.lib.orc_affinity_count())
+
+    def sat_batch_mt(self, r1, r2, reps=1, threads=1):
+        """convex_collide over all pairs, `reps` times, on `threads` threads (BASELINE.md 4a run C1)."""
+        r1, r2 = _f32(r1).reshape(-1, 8), _f32(r2).reshape(-1, 8)
+        out = np.zeros(r1.shape[0], np.uint8)
+        self.lib.orc_sat_batch_mt(r1.ctypes.data, r2.ctypes.data, r1.shape[0], out.ctypes.data, int(reps), int(threads))
+        return out
+
+    def count_streamed_mt(self, pair, z, threads=1):
+        """one pair on shared normals, the sample range split over `threads` threads (run C2)."""
+        p = np.ascontiguousarray(pair, dtype=PAIR_DTYPE).reshape(1)
+        z = _f32(z)
+        ndof, ldz = z.shape
+        return int(self.lib.orc_count_streamed_mt(p.ctypes.data, z.ctypes.data, ldz, ndof, ldz, int(threads)))
 
     def get_bin(self, p, bins):
         b = _f32(list(bins) + [0.0])                 # one readable entry past the end (utils.cu:202)

@@ -58,9 +58,14 @@ def test_header_is_valid_c_and_links_from_c(satmc, tmp_path):
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", satmc.INCLUDE_DIR,
                            os.path.join(root, "tests", "c", "abi_example.c"), "-o", exe, "-L", libdir, "-lsatmc", "-lm",
                            f"-Wl,-rpath,{libdir}"])
+    exe2 = str(tmp_path / "group_example")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", satmc.INCLUDE_DIR,
+                           os.path.join(root, "tests", "c", "group_example.c"), "-o", exe2, "-L", libdir, "-lsatmc", "-lm",
+                           f"-Wl,-rpath,{libdir}"])
     import torch
-    r = subprocess.run([exe], capture_output=True, text=True)
-    if torch.cuda.is_available():
-        assert r.returncode == 0, r.stdout + r.stderr
-    else:
-        assert r.returncode == 77, r.stdout + r.stderr       # fails loudly without a GPU
+    for e in (exe, exe2):
+        r = subprocess.run([e], capture_output=True, text=True)
+        if torch.cuda.is_available():
+            assert r.returncode == 0, r.stdout + r.stderr
+        else:
+            assert r.returncode == 77, r.stdout + r.stderr   # fails loudly without a GPU

@@ -392,7 +392,7 @@ def test_dynamic_work_distribution_is_invisible(ctx, dev, oracle, workloads):
     d_sw = dev.zeros(64 * 2, np.uint64)
     for rep in range(3):
         fused(ctx, dev, big[:1], 3_000_000, 9)                       # block-uniform: static order, no tickets
-        ctx.count_fused_sweep(dev.put(big[:64]), 64, dev.put(sig.ravel()), 2, 10_000, 3, d_sw)
+        ctx.count_fused_sweep(dev.put(big[:64]), 64, sig, 2, 10_000, 3, d_sw)
         fused(ctx, dev, big[: 2_369 * (rep + 1)], 300, 8)            # just above / well above one item per warp
         np.testing.assert_array_equal(fused(ctx, dev, big, 2_500, 31), first)
         np.testing.assert_array_equal(fused(ctx, dev, five, 1_027, 32, sample_offset=5), first5)
@@ -508,7 +508,7 @@ def test_sweep_equals_fused_per_setting(ctx, dev, workloads, n, offset, theta_le
     if theta_levels:
         sig[:, 2] = rng.choice(np.array([0.0, 0.21, 0.5], np.float32), n_cov)
     sig[0] = 0.0                                                     # a setting with no uncertainty at all
-    d_pairs = dev.put(pairs); d_sig = dev.put(sig.ravel())
+    d_pairs = dev.put(pairs); d_sig = sig          # settings are a host array
     for flags in (0, EXACT):
         d_hits = dev.zeros(pairs.size * n_cov, np.uint64)
         ctx.count_fused_sweep(d_pairs, pairs.size, d_sig, n_cov, n, 321, d_hits, sample_offset=offset, pair_id_offset=11, flags=flags)
@@ -535,7 +535,7 @@ def test_sweep_cfg5_full_size(ctx, dev, workloads):
     sig = np.sqrt(np.stack([vx.ravel(), vy.ravel(), vt.ravel()], 1)).astype(np.float32)
     n = 100_000
     d_hits = dev.zeros(base.size * 64, np.uint64)
-    ctx.count_fused_sweep(dev.put(base), base.size, dev.put(sig.ravel()), 64, n, 77, d_hits)
+    ctx.count_fused_sweep(dev.put(base), base.size, sig, 64, n, 77, d_hits)
     ctx.synchronize()
     k_sweep = dev.get(d_hits, np.uint64).astype(np.float64)
     rows = workloads.variance_sweep_pairs(10_000, seed=5)

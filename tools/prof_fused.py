@@ -12,7 +12,7 @@ if mode == "sweep":
     base = wl.dataset_pairs(10_000, 5)
     grid = np.array([0.01, 0.05, 0.15, 0.3]); vx, vy, vt = np.meshgrid(grid, grid, grid, indexing="ij")
     sig = np.sqrt(np.stack([vx.ravel(), vy.ravel(), vt.ravel()], 1)).astype(np.float32)
-    d_pairs = put(base); d_s = torch.from_numpy(sig.ravel()).cuda(); d_hits = torch.zeros(base.size * 64, dtype=torch.int64, device="cuda")
+    d_pairs = put(base); d_s = sig; d_hits = torch.zeros(base.size * 64, dtype=torch.int64, device="cuda")
     for _ in range(3):
         ctx.count_fused_sweep(d_pairs, base.size, d_s, 64, 20_000, 7, d_hits)
 elif mode == "poly":

@@ -80,7 +80,7 @@ def main():
         base = wl.dataset_pairs(10_000, 5)
         grid = np.array([0.01, 0.05, 0.15, 0.3]); vx, vy, vt = np.meshgrid(grid, grid, grid, indexing="ij")
         sig = np.sqrt(np.stack([vx.ravel(), vy.ravel(), vt.ravel()], 1)).astype(np.float32)
-        d_b = put(base); d_s = torch.from_numpy(sig.ravel()).cuda(); d_h = torch.zeros(base.size * 64, dtype=torch.int64, device="cuda")
+        d_b = put(base); d_s = sig; d_h = torch.zeros(base.size * 64, dtype=torch.int64, device="cuda")
         ctx.exact_evals(reset=True)
         best, med = time_call(lambda: ctx.count_fused_sweep(d_b, base.size, d_s, 64, 100_000, 7, d_h), reps=3)
         print(f"fused sweep cfg5 1e4 pairs x 64 cov x 1e5: best {best:.3f} ms {base.size * 64 * 1e5 / best / 1e6:.2f} Gtests/s "
