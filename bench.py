@@ -62,7 +62,7 @@ def sass_constants():
         with open(path) as f:
             d = json.load(f)
         for name, k in d["kernels"].items():
-            if "DirectSrc, false, false" not in name:
+            if "DirectSrc, false, false, false" not in name:
                 continue
             for L in k["loops"]:
                 if 45 <= L["imad_wide"] <= 60:

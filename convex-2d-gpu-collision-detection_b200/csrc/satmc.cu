@@ -129,6 +129,9 @@ int satmc_create(int device, void* stream, satmc_ctx** out)
         return rc;
     }
     ctx->d_blocks_done = reinterpret_cast<unsigned*>(ctx->d_ticket + 2);
+    // development knobs (multiples of 128 samples)
+    if (const char* e = getenv("SATMC_MIN_CHUNK")) { const long v = atol(e); if (v >= 128) ctx->tune_min_chunk = (uint64_t)v / 128 * 128; }
+    if (const char* e = getenv("SATMC_TINY_CHUNK")) { const long v = atol(e); if (v >= 128) ctx->tune_tiny_chunk = (uint64_t)v / 128 * 128; }
     *out = ctx;
     return SATMC_OK;
 }
@@ -208,8 +211,8 @@ static int plan_items(satmc_ctx* ctx, CountParams& p, int bps, uint64_t& blocks,
 {
     const uint64_t resident_warps = (uint64_t)ctx->sm_count * bps * kWarps;
     const uint64_t target_items = resident_warps * (uint64_t)items_per_warp;
-    const uint64_t min_chunk = 2048;                              // 64 samples per lane: amortises the pair prologue
-    const uint64_t tiny_chunk = 256;                              // small problems: parallelism matters more than the prologue
+    const uint64_t min_chunk = ctx->tune_min_chunk;               // 64 samples per lane: amortises the pair prologue
+    const uint64_t tiny_chunk = ctx->tune_tiny_chunk;             // small problems: parallelism matters more than the prologue
     uint64_t n_chunks = 1;
     if (p.n_pairs < target_items) {
         n_chunks = (target_items + p.n_pairs - 1) / p.n_pairs;
@@ -345,10 +348,14 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
         else if (tma)
             k_count_streamed_tma<3><<<(unsigned)blocks, kThreads, tma_smem_bytes(3), ctx->stream>>>(src, p, zmap);
         else
-            k_count<Src, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
+            if (p.acc) k_count<Src, true, false, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
+            else k_count<Src, true, false, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
     } else {
-        if (defer) k_count<Src, false, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
-        else k_count<Src, false, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
+        const bool multi = p.acc != nullptr;                         // several work items per counter (prepare_counters)
+        if (defer && multi) k_count<Src, false, true, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
+        else if (defer) k_count<Src, false, true, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
+        else if (multi) k_count<Src, false, false, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
+        else k_count<Src, false, false, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
     }
     if (cudaPeekAtLastError() != cudaSuccess) ctx->ticket_next[ctx->ticket_sel] = ticket_before;       // nothing ran: no ticket was drawn
     CU(ctx, cudaGetLastError());
@@ -380,7 +387,7 @@ int satmc_count_fused(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pair
     if (n_pairs > 0xffffffffull - pair_id_offset) return fail(ctx, SATMC_ERR_INVALID, "pair ids exceed 32 bits");
     if (((uintptr_t)d_pairs & 15u) != 0) return fail(ctx, SATMC_ERR_INVALID, "d_pairs must be 16-byte aligned");
     DeviceGuard g(ctx->device);
-    CountParams p{}; p.pair_id_stride = 1;
+    CountParams p{};
     p.n_pairs = n_pairs; p.n_samples = n_samples; p.sample_offset = sample_offset; p.pair_id_offset = pair_id_offset;
     philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), p.keys); p.flags = flags;
     p.hits = reinterpret_cast<unsigned long long*>(d_hits); p.exact_evals = ctx->d_exact_evals;
@@ -394,7 +401,7 @@ int satmc_count_streamed(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_p
     if (rc) return rc;
     if (((uintptr_t)d_pairs & 15u) != 0) return fail(ctx, SATMC_ERR_INVALID, "d_pairs must be 16-byte aligned");
     DeviceGuard g(ctx->device);
-    CountParams p{}; p.pair_id_stride = 1;
+    CountParams p{};
     p.n_pairs = n_pairs; p.n_samples = n_samples; p.flags = flags;
     p.hits = reinterpret_cast<unsigned long long*>(d_hits); p.exact_evals = ctx->d_exact_evals;
     p.z = d_z; p.ldz = ldz; p.z_pair_stride = z_pair_stride; p.ndof = ndof;
@@ -484,7 +491,7 @@ int satmc_count_fused_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs, u
     if ((!d_pairs || !d_hits) && n_pairs) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
     if (n_pairs > 0xffffffffull - pair_id_offset) return fail(ctx, SATMC_ERR_INVALID, "pair ids exceed 32 bits");
     DeviceGuard g(ctx->device);
-    CountParams p{}; p.pair_id_stride = 1;
+    CountParams p{};
     p.n_pairs = n_pairs; p.n_samples = n_samples; p.sample_offset = sample_offset; p.pair_id_offset = pair_id_offset;
     philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), p.keys); p.flags = flags & (SATMC_ACCUMULATE | SATMC_EXACT_ONLY); p.exact_evals = ctx->d_exact_evals;
     p.hits = reinterpret_cast<unsigned long long*>(d_hits);
@@ -512,7 +519,7 @@ int satmc_count_streamed_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs
     int rc = check_streamed_args(ctx, d_pairs, d_z, ldz, 3, n_samples, n_pairs, z_pair_stride, d_hits);
     if (rc) return rc;
     DeviceGuard g(ctx->device);
-    CountParams p{}; p.pair_id_stride = 1;
+    CountParams p{};
     p.n_pairs = n_pairs; p.n_samples = n_samples; p.flags = flags & (SATMC_ACCUMULATE | SATMC_EXACT_ONLY); p.exact_evals = ctx->d_exact_evals;
     p.hits = reinterpret_cast<unsigned long long*>(d_hits);
     p.z = d_z; p.ldz = ldz; p.z_pair_stride = z_pair_stride; p.ndof = 3;
@@ -548,7 +555,7 @@ int satmc_count_fused_sweep(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t 
         if (!(flags & SATMC_ACCUMULATE)) CU(ctx, cudaMemsetAsync(d_hits, 0, n_pairs * n_cov * sizeof(uint64_t), ctx->stream));
         return SATMC_OK;
     }
-    CountParams p{}; p.pair_id_stride = 1;
+    CountParams p{};
     p.n_pairs = n_pairs; p.n_samples = n_samples; p.sample_offset = sample_offset; p.pair_id_offset = pair_id_offset;
     philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), p.keys);
     p.flags = flags;
@@ -607,11 +614,11 @@ static int mc_step_impl(satmc_ctx* ctx, const float* d_robot_base, const float* 
     void* d_hits = nullptr;
     int rc = scratch(ctx, 0, (size_t)num_left * sizeof(unsigned long long), &d_hits);
     if (rc) return rc;
-    CountParams p{}; p.pair_id_stride = stream_id_stride;
+    CountParams p{};
     p.n_pairs = (uint64_t)num_left; p.n_samples = (uint64_t)n_batch; p.sample_offset = (uint64_t)(n_samples - n_batch);
     p.pair_id_offset = stream_id_offset; philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), p.keys); p.flags = 0;
     p.hits = reinterpret_cast<unsigned long long*>(d_hits); p.exact_evals = ctx->d_exact_evals;
-    IndirectSrc src{d_robot_base, d_poses, d_std_devs, d_pose_idxs, d_std_dev_idxs, d_positions, n_poses, n_std, d_live};
+    IndirectSrc src{d_robot_base, d_poses, d_std_devs, d_pose_idxs, d_std_dev_idxs, d_positions, n_poses, n_std, d_live, stream_id_stride};
     rc = launch_count<IndirectSrc, false>(ctx, src, p, ctx->profiling);
     if (rc) return rc;
     if (ar) {

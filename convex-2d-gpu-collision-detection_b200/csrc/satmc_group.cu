@@ -298,7 +298,7 @@ int satmc_group_create_rank(const void* unique_id, int world, int rank, int devi
     if (!g) return gfail(nullptr, SATMC_ERR_NOMEM, "out of host memory");
     RestoreDevice restore;
     g->world = world; g->rank0 = rank;
-    int rc = add_local(g, device, stream, stream == nullptr);
+    int rc = add_local(g, device, stream, false);      // NULL = the legacy default stream, as in satmc_create
     if (rc == SATMC_OK && world > 1) {
         NcclApi* N = nccl_api();
         if (!N->ok) rc = gfail(g, SATMC_ERR_NCCL, "NCCL unavailable: %s", N->why);

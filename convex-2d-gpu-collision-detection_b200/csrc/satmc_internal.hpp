@@ -43,6 +43,7 @@ struct satmc_ctx {
     size_t acc_cap[2] = {0, 0};
     unsigned* d_blocks_done = nullptr;
     int* h_word = nullptr;                   // pinned: the adaptive loop's "pairs left" comes back here
+    uint64_t tune_min_chunk = 2048, tune_tiny_chunk = 256;   // planner: samples per work item (see plan_items)
 };
 
 // State of one adaptive z-test loop (satmc_adaptive_run) on one context, in steps: begin, then while pending

@@ -45,6 +45,7 @@ constexpr int kWarps = kThreads / 32;
 struct DirectSrc {
     const satmc_pair* pairs;
     __device__ __forceinline__ uint64_t element(uint64_t slot) const { return slot; }
+    __device__ __forceinline__ uint32_t stream_id(uint64_t elem) const { return (uint32_t)elem; }
     // the robot is create_rect(rw, rh) by construction: the screening pass always applies
     __device__ __forceinline__ bool robot_is_centred_rect() const { return true; }
     __device__ __forceinline__ void robot_base8(const float v[12], float b[8]) const { rect_base(v[3], v[4], b); }
@@ -63,7 +64,9 @@ struct IndirectSrc {
     const float* pose_idxs; const float* std_dev_idxs; const float* positions;
     uint32_t n_poses, n_std;
     const int* live;               // optional: slot -> pair id (device-side work list of unfinished pairs)
+    uint32_t stream_stride;        // Philox stream of element e = pair_id_offset + e * stream_stride (rows dealt round-robin to GPUs)
     __device__ __forceinline__ uint64_t element(uint64_t slot) const { return live ? (uint64_t)__ldg(live + slot) : slot; }
+    __device__ __forceinline__ uint32_t stream_id(uint64_t elem) const { return (uint32_t)elem * stream_stride; }
     // The reference kernel transforms whatever 8 floats robot_base holds (ztest.cu:148-149).  Its mains always upload
     // create_rect(robot_w, robot_h) (ztest.cu:297), which is what the screening pass assumes (centre / half extents);
     // any other quad is honoured by evaluating every sample of the launch with the exact arithmetic on the 8 corners
@@ -110,8 +113,6 @@ struct CountParams {
     // dynamic work distribution (null = static grid-stride): a warp's first item is its global warp index, every further
     // one is drawn from a device counter that only ever grows; ticket_base is its value when this launch starts
     unsigned long long* ticket; unsigned long long ticket_base;
-    // Philox stream of array element e = pair_id_offset + e * pair_id_stride (stride > 1: rows dealt round-robin to GPUs)
-    uint32_t pair_id_stride;
     // Several work items per counter (n_chunks > 1): contributions are added atomically to `acc`, a scratch array of
     // the context that holds zeros between launches, and the last block to finish moves the totals to `hits` and
     // leaves `acc` and `blocks_done` zero again -- one launch, no memset (finalize_counters).  Counter i of the launch
@@ -122,12 +123,17 @@ struct CountParams {
 };
 
 // where the atomics of a launch go
+#ifdef SATMC_EXP_NOFINAL
+__device__ __forceinline__ unsigned long long* counter_base(const CountParams& p) { return p.hits; }
+#else
 __device__ __forceinline__ unsigned long long* counter_base(const CountParams& p) { return p.acc ? p.acc : p.hits; }
+#endif
 
 // End of every counting kernel.  All threads of the block must call it (it contains barriers).
-__device__ __forceinline__ void finalize_counters(const CountParams& p)
+// Out of line on purpose: inlined, its barriers and the extra live launch parameters changed ptxas's schedule of the
+// fused hot loop (same instruction mix, 2 % slower; profiles/r2_codegen_experiments.log).
+__device__ __noinline__ void finalize_counters_slow(const CountParams& p)
 {
-    if (p.acc == nullptr) return;                                     // launch-uniform
     __shared__ unsigned s_last;
     __syncthreads();                                                  // this block's atomics are issued
     if (threadIdx.x == 0) {
@@ -144,6 +150,14 @@ __device__ __forceinline__ void finalize_counters(const CountParams& p)
         if (p.flags & SATMC_ACCUMULATE) p.hits[off] += v; else p.hits[off] = v;
     }
     if (threadIdx.x == 0) *p.blocks_done = 0u;
+}
+
+__device__ __forceinline__ void finalize_counters(const CountParams& p)
+{
+#ifdef SATMC_EXP_NOFINAL
+    return;
+#endif
+    if (p.acc != nullptr) finalize_counters_slow(p);                  // launch-uniform
 }
 
 // Next work item of a warp.  `drawn` is the ticket lane 0 took while the warp was busy with the current item.
@@ -368,7 +382,7 @@ __device__ __forceinline__ unsigned streamed_chunk(const PairConst& P, const Pai
 // same code the immediate path uses, add the count to the pair's counter.  Entries may belong to earlier items of
 // this warp; their counters were stored before (plain store or atomic, ordered by __syncwarp), so an atomic add is right.
 template <class Src>
-__device__ __noinline__ void cold_flush(ColdQueue* Qp, const Src& src, const CountParams& p, int lane)
+__device__ __noinline__ void cold_flush(ColdQueue* Qp, const Src& src, const CountParams& p, int lane, unsigned long long* counters)
 {
     ColdQueue& Q = *Qp;
     __syncwarp();
@@ -385,20 +399,25 @@ __device__ __noinline__ void cold_flush(ColdQueue* Qp, const Src& src, const Cou
         src.robot_base8(v, base);
         exact_robot_corners(v[0], v[1], P.ca, P.sa, base, robot);
         if (!src.robot_is_centred_rect()) { P.eps = CUDART_INF_F; P.eps_b = CUDART_INF_F; }
-        const uint32_t pid = p.pair_id_offset + (uint32_t)elem * p.pair_id_stride;
+        const uint32_t pid = p.pair_id_offset + src.stream_id(elem);
         const unsigned c = (v[10] == 0.0f && v[11] == 0.0f) ? fused_group_slow<3>(P, robot, g, 0xFu, pid, p.keys, p.exact_evals)
                                                            : fused_group_slow<5>(P, robot, g, 0xFu, pid, p.keys, p.exact_evals);
         SATMC_ASSERT(slot < p.hits_len);
-        if (c) atomicAdd(counter_base(p) + slot, (unsigned long long)c);
+        if (c) atomicAdd(counters + slot, (unsigned long long)c);
     }
     __syncwarp();
     if (lane == 0) Q.n = 0;
     __syncwarp();
 }
 
-template <class Src, bool STREAMED, bool DEFER = false>
+// MULTI: several work items per counter (n_chunks > 1) -- atomics into the zero-invariant scratch + finalize_counters.
+// A separate instantiation, so that the one-item-per-pair kernels (cfg 3, the adaptive loop) carry none of that code:
+// its mere presence changes ptxas's schedule of the fused hot loop (same instruction mix, 1-2 % slower;
+// profiles/r2_codegen_experiments.log).
+template <class Src, bool STREAMED, bool DEFER = false, bool MULTI = false>
 __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED : SATMC_MIN_BLOCKS_FUSED) k_count(const __grid_constant__ Src src, const __grid_constant__ CountParams p)
 {
+    unsigned long long* const counters = MULTI ? p.acc : p.hits;
     __shared__ float s_robot[kWarps][8];
     __shared__ PairConst s_pair[kWarps];
     __shared__ unsigned s_part[kWarps];
@@ -437,13 +456,15 @@ __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED
             cnt = (p.ndof == 5) ? streamed_chunk<5>(P, Pc, s_robot[warp], z, p.ldz, c_len, p.vec_ok, lane, ev)
                                 : streamed_chunk<3>(P, Pc, s_robot[warp], z, p.ldz, c_len, p.vec_ok, lane, ev);
         } else {
-            const uint32_t pid = p.pair_id_offset + (uint32_t)elem * p.pair_id_stride;
+            const uint32_t pid = p.pair_id_offset + src.stream_id(elem);
             const uint64_t s_begin = p.sample_offset + c_begin;
             const bool dof3 = (v[10] == 0.0f) && (v[11] == 0.0f);
             cnt = dof3 ? fused_chunk<3, DEFER>(P, Pc, s_robot[warp], s_begin, s_begin + c_len, pid, p.keys, lane, ev, Q, (unsigned)pair)
                        : fused_chunk<5, DEFER>(P, Pc, s_robot[warp], s_begin, s_begin + c_len, pid, p.keys, lane, ev, Q, (unsigned)pair);
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
+        // (the non-MULTI instantiation keeps both branches although the host never sets block_uniform or n_chunks > 1
+        // for it: without them ptxas schedules the fused hot loop differently and it runs 2 % slower)
         if (p.block_uniform) {
             if (lane == 0) s_part[warp] = cnt;
             __syncthreads();
@@ -451,24 +472,24 @@ __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED
                 unsigned long long t = 0;
 #pragma unroll
                 for (int w = 0; w < kWarps; w++) t += s_part[w];
-                atomicAdd(counter_base(p) + pair, t);              // one atomic per block
+                atomicAdd(counters + pair, t);                     // one atomic per block
             }
             __syncthreads();
         } else if (lane == 0) {
             if (p.n_chunks == 1) {
                 if (p.flags & SATMC_ACCUMULATE) p.hits[pair] += cnt; else p.hits[pair] = cnt;
             } else {
-                atomicAdd(counter_base(p) + pair, (unsigned long long)cnt);
+                atomicAdd(counters + pair, (unsigned long long)cnt);
             }
         }
         if (DEFER && Q != nullptr) {
             __syncwarp();
-            if (Q->n >= 32u) cold_flush(Q, src, p, lane);            // enough for a full pass
+            if (Q->n >= 32u) cold_flush(Q, src, p, lane, counters);  // enough for a full pass
         }
         item = next_item(p, item, stride, drawn);
     }
-    if (DEFER && Q != nullptr) cold_flush(Q, src, p, lane);
-    finalize_counters(p);
+    if (DEFER && Q != nullptr) cold_flush(Q, src, p, lane, counters);
+    if (MULTI) finalize_counters_slow(p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -775,7 +796,7 @@ __global__ void __launch_bounds__(32 * sweep_warps(SHARE), 2) k_count_sweep(cons
         const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
         const uint64_t c_len = (c_begin + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - c_begin);
         unsigned long long* ev = (p.flags & SATMC_EXACT_ONLY) ? nullptr : p.exact_evals;
-        const uint32_t pid = p.pair_id_offset + (uint32_t)pair * p.pair_id_stride;
+        const uint32_t pid = p.pair_id_offset + (uint32_t)pair;
         const uint64_t b = p.sample_offset + c_begin, e = b + c_len;
         const uint64_t q_lo = (b + 7) >> 3, q_hi = e >> 3;              // full 8-sample super-groups [q_lo, q_hi)
         if (SHARE && q_lo <= q_hi) {
@@ -907,7 +928,7 @@ __device__ __forceinline__ unsigned poly_chunk(const PolyPairShared& S, const Po
             if (fill >= 32u) cnt += poly_queue_drain<NR, NO>(S, R, Q, fill, false, lane, ev);
         }
     } else {
-        const uint32_t pid = p.pair_id_offset + (uint32_t)pair * p.pair_id_stride;
+        const uint32_t pid = p.pair_id_offset + (uint32_t)pair;
         const uint64_t b = p.sample_offset + c_begin, e = b + c_len;
         const uint64_t g_end = (e + 3) >> 2;
         for (uint64_t g0 = b >> 2; g0 < g_end; g0 += 32) {               // 4-sample groups, ragged ends masked

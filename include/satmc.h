@@ -274,6 +274,7 @@ int satmc_shard_range(int shard_mode, uint64_t n_units, int world, int rank, uin
 
 int satmc_group_create(const int* devices /* NULL = 0..n_dev-1 */, int n_dev, satmc_group** out);
 int satmc_group_unique_id(void* out /* SATMC_UNIQUE_ID_BYTES */);
+/* `stream`: the cudaStream_t this rank's work and collectives are enqueued on (NULL = the legacy default stream). */
 int satmc_group_create_rank(const void* unique_id, int world, int rank, int device, void* stream, satmc_group** out);
 int satmc_group_destroy(satmc_group* g);
 int satmc_group_synchronize(satmc_group* g);

@@ -4,7 +4,7 @@
     python tools/sass_count.py [--lib PATH] [--kernel SUBSTR] [--json OUT] [--dump OUT.txt]
 
 For every kernel whose (demangled) name contains SUBSTR (default: the fused counting kernel
-`k_count<satmc::DirectSrc, false, false>`) the script disassembles the function with `cuobjdump -sass`,
+`k_count<satmc::DirectSrc, false, false, false>`) the script disassembles the function with `cuobjdump -sass`,
 finds the loops (a backward branch closes a loop: [target, branch]) and reports, for every innermost
 loop with at least --min-instr instructions: total instructions, and counts of IMAD.WIDE, other integer
 multiply-adds, FP32 (FFMA/FMUL/FADD/FMNMX/FSETP/FSEL), MUFU, LOP3/shift/PRMT, I2F/F2I conversions, loads /
@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import argparse
 import collections
+import hashlib
 import json
 import os
 import re
@@ -112,7 +113,9 @@ def summarise(instrs, s, e):
     body = instrs[s:e + 1]
     cnt = collections.Counter(classify(op, rest) for _, op, rest in body)
     ops = collections.Counter(op.split(".")[0] for _, op, _ in body)
+    text = "\n".join(op + re.sub(r"0x[0-9a-f]+", "X", rest) for _, op, rest in body)       # schedule and register assignment
     return {"start": hex(body[0][0]), "end": hex(body[-1][0]), "instr": len(body), "classes": dict(sorted(cnt.items())),
+            "fingerprint": hashlib.sha1(text.encode()).hexdigest()[:16],
             "imad_wide": cnt.get("IMAD.WIDE", 0), "fp32": cnt.get("FP32", 0), "mufu": cnt.get("MUFU", 0),
             "local_spill": cnt.get("LOCAL(spill)", 0),
             "opcodes": dict(sorted(ops.items(), key=lambda kv: -kv[1]))}
@@ -121,7 +124,7 @@ def summarise(instrs, s, e):
 def main():
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--lib", default=DEFAULT_LIB)
-    ap.add_argument("--kernel", default="k_count<satmc::DirectSrc, false, false>")
+    ap.add_argument("--kernel", default="k_count<satmc::DirectSrc, false, false, false>")
     ap.add_argument("--min-instr", type=int, default=60)
     ap.add_argument("--json", default=None)
     ap.add_argument("--dump", default=None, help="write the SASS of the reported loops here")
