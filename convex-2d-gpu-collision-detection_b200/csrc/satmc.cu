@@ -337,6 +337,10 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
     const bool defer = !STREAMED && p.chunk >= 32768;
     rc = prepare_counters(ctx, p, p.n_pairs, p.n_pairs);
     if (rc) return rc;
+    // k_count without the deferred queue: every counter receives a known number of contributions (packed_arrive)
+    p.arrivals = p.block_uniform ? p.n_chunks / kWarps : p.n_chunks;
+    if (p.acc && !defer && !tma && (p.n_chunks >= (1u << 24) || p.chunk * (uint64_t)p.n_chunks >= (1ull << kPackShift)))
+        return fail(ctx, SATMC_ERR_INVALID, "sample range too long for one call (%llu samples per pair)", (unsigned long long)p.n_samples);
     const uint64_t ticket_before = ctx->ticket_next[ctx->ticket_sel];
     // bulk-copy staged kernel: dynamic order only when all pairs read one shared bank (L2 resident, issue bound: +5 %);
     // with private banks the kernel is HBM bound and the static order streams DRAM slightly better (measured -1..2 %)
