@@ -22,7 +22,8 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsatmc.so")
+#: SATMC_LIB selects another build of the same sources (the -DSATMC_DEBUG library with device-side bounds asserts)
+LIB_PATH = os.environ.get("SATMC_LIB") or os.path.join(_HERE, "libsatmc.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
 
 SATMC_ACCUMULATE = 0x1

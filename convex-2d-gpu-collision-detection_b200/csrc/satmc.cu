@@ -77,7 +77,11 @@ static int scratch(satmc_ctx* ctx, int slot, size_t bytes, void** out)
 
 extern "C" {
 
-const char* satmc_version(void) { return "satmc-b200 0.1 (sm_100a)"; }
+#ifdef SATMC_DEBUG
+const char* satmc_version(void) { return "satmc-b200 0.2 (sm_100a) DEBUG: device-side bounds asserts"; }
+#else
+const char* satmc_version(void) { return "satmc-b200 0.2 (sm_100a)"; }
+#endif
 
 const char* satmc_last_error(const satmc_ctx* ctx) { return ctx ? ctx->err : satmc_thread_error(); }
 
@@ -860,22 +864,32 @@ static int count_fused_host_pipelined(satmc_ctx* ctx, const satmc_pair* h_pairs,
     if (flags & SATMC_ACCUMULATE)
         CU(ctx, cudaMemcpyAsync(d_hits + lead, h_hits + lead, rest * sizeof(uint64_t), cudaMemcpyHostToDevice, B));
     ctx->events_by_caller = true;
-    CU(ctx, cudaEventRecord(ctx->ev0, A));
-    int rc = satmc_count_fused(ctx, d_pairs, lead, n_samples, seed, sample_offset, pair_id_offset, d_hits, flags);
+    int rc = SATMC_OK;
+    cudaError_t ce = cudaEventRecord(ctx->ev0, A);
+    if (ce != cudaSuccess) rc = fail(ctx, SATMC_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(ce));
+    if (rc == SATMC_OK) rc = satmc_count_fused(ctx, d_pairs, lead, n_samples, seed, sample_offset, pair_id_offset, d_hits, flags);
     if (rc == SATMC_OK) {
-        cudaMemcpyAsync(h_hits, d_hits, lead * sizeof(uint64_t), cudaMemcpyDeviceToHost, A);
+        ce = cudaMemcpyAsync(h_hits, d_hits, lead * sizeof(uint64_t), cudaMemcpyDeviceToHost, A);
+        if (ce != cudaSuccess) rc = fail(ctx, SATMC_ERR_CUDA, "cudaMemcpyAsync (lead counters) failed: %s", cudaGetErrorString(ce));
+    }
+    if (rc == SATMC_OK) {
         ctx->stream = B; ctx->ticket_sel = 1;
         rc = satmc_count_fused(ctx, d_pairs + lead, rest, n_samples, seed, sample_offset, pair_id_offset + (uint32_t)lead,
                                d_hits + lead, flags);
         ctx->stream = A; ctx->ticket_sel = 0;
     }
     ctx->events_by_caller = false;
-    if (rc == SATMC_OK) cudaMemcpyAsync(h_hits + lead, d_hits + lead, rest * sizeof(uint64_t), cudaMemcpyDeviceToHost, B);
-    cudaEventRecord(ctx->ev_join, B);                                // always rejoin, also after an error
-    cudaStreamWaitEvent(A, ctx->ev_join, 0);
-    cudaEventRecord(ctx->ev1, A);
+    if (rc == SATMC_OK) {
+        ce = cudaMemcpyAsync(h_hits + lead, d_hits + lead, rest * sizeof(uint64_t), cudaMemcpyDeviceToHost, B);
+        if (ce != cudaSuccess) rc = fail(ctx, SATMC_ERR_CUDA, "cudaMemcpyAsync (rest counters) failed: %s", cudaGetErrorString(ce));
+    }
+    // always rejoin the two streams, also after an error; a failure here is reported unless an earlier one already is
+    cudaError_t cj = cudaEventRecord(ctx->ev_join, B);
+    if (cj == cudaSuccess) cj = cudaStreamWaitEvent(A, ctx->ev_join, 0);
+    if (cj == cudaSuccess) cj = cudaEventRecord(ctx->ev1, A);
+    if (cj != cudaSuccess && rc == SATMC_OK) rc = fail(ctx, SATMC_ERR_CUDA, "rejoining the streams failed: %s", cudaGetErrorString(cj));
     ctx->last_ms_valid = (rc == SATMC_OK);
-    if (rc) { cudaStreamSynchronize(A); return rc; }
+    if (rc) { cudaStreamSynchronize(B); cudaStreamSynchronize(A); cudaGetLastError(); return rc; }
     CU(ctx, cudaStreamSynchronize(A));
     CU(ctx, cudaGetLastError());
     return SATMC_OK;

@@ -182,10 +182,29 @@ void free_group(satmc_group* g)
     delete g;
 }
 
+// single-process groups: ncclCommInitAll over the local devices, on first use
+int ensure_comms(satmc_group* g)
+{
+    if (g->world == 1 || g->dev[0].comm != nullptr) return SATMC_OK;
+    NcclApi* N = nccl_api();
+    if (!N->ok) return gfail(g, SATMC_ERR_NCCL, "NCCL unavailable: %s", N->why);
+    const int n = (int)g->dev.size();
+    if (n != g->world) return gfail(g, SATMC_ERR_NCCL, "internal: communicator missing");   // create_rank initialises eagerly
+    std::vector<ncclComm_t> comms(n);
+    std::vector<int> ids(n);
+    for (int i = 0; i < n; i++) ids[i] = g->dev[i].ctx->device;
+    ncclResult_t r = N->CommInitAll(comms.data(), n, ids.data());
+    if (r != ncclSuccess) return gfail(g, SATMC_ERR_NCCL, "ncclCommInitAll failed: %s", N->GetErrorString(r));
+    for (int i = 0; i < n; i++) g->dev[i].comm = comms[i];
+    return SATMC_OK;
+}
+
 // all-reduce(SUM) of n 64-bit counters, in place, on every local device (sample-range sharding)
 int all_reduce_u64(satmc_group* g, std::vector<void*>& bufs, size_t n)
 {
     if (g->world == 1) return SATMC_OK;
+    int rc = ensure_comms(g);
+    if (rc) return rc;
     NcclApi* N = nccl_api();
     GNCCL(g, N->GroupStart());
     for (size_t l = 0; l < g->dev.size(); l++)
@@ -198,6 +217,8 @@ int all_reduce_u64(satmc_group* g, std::vector<void*>& bufs, size_t n)
 int all_gather(satmc_group* g, std::vector<void*>& bufs, size_t chunk, size_t elem_bytes)
 {
     if (g->world == 1) return SATMC_OK;
+    int rc = ensure_comms(g);
+    if (rc) return rc;
     NcclApi* N = nccl_api();
     GNCCL(g, N->GroupStart());
     for (size_t l = 0; l < g->dev.size(); l++) {
@@ -258,18 +279,8 @@ int satmc_group_create(const int* devices, int n_dev, satmc_group** out)
     g->world = n_dev; g->rank0 = 0;
     int rc = SATMC_OK;
     for (int i = 0; i < n_dev && rc == SATMC_OK; i++) rc = add_local(g, devices ? devices[i] : i, nullptr, true);
-    if (rc == SATMC_OK && n_dev > 1) {
-        NcclApi* N = nccl_api();
-        if (!N->ok) rc = gfail(g, SATMC_ERR_NCCL, "NCCL unavailable: %s", N->why);
-        else {
-            std::vector<ncclComm_t> comms(n_dev);
-            std::vector<int> ids(n_dev);
-            for (int i = 0; i < n_dev; i++) ids[i] = g->dev[i].ctx->device;
-            ncclResult_t r = N->CommInitAll(comms.data(), n_dev, ids.data());
-            if (r != ncclSuccess) rc = gfail(g, SATMC_ERR_NCCL, "ncclCommInitAll failed: %s", N->GetErrorString(r));
-            else for (int i = 0; i < n_dev; i++) g->dev[i].comm = comms[i];
-        }
-    }
+    // the communicators are created by the first call that needs a collective (ensure_comms): the adaptive path and
+    // host-buffer calls sharded by pair read every slice from the device that computed it and never pay for NCCL
     if (rc != SATMC_OK) { snprintf(satmc_thread_error(), 512, "%s", g->err); free_group(g); return rc; }
     *out = g;
     return SATMC_OK;

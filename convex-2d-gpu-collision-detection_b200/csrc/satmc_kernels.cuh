@@ -239,7 +239,7 @@ __device__ __noinline__ unsigned fused_group_cold(ColdQueue* Q, unsigned pair_sl
 {
     if (Q != nullptr) {
         const unsigned slot = atomicAdd(&Q->n, 1u);
-        if (slot < kColdCap) { Q->pair[slot] = pair_slot; Q->g[slot] = g; return 0u; }
+        if (slot < kColdCap) { SATMC_ASSERT(pair_slot < 0xffffffffu); Q->pair[slot] = pair_slot; Q->g[slot] = g; return 0u; }
     }
     return fused_group_slow<D>(Pcold, robot, g, 0xFu, pid, K, exact_evals);
 }
@@ -798,6 +798,7 @@ __global__ void __launch_bounds__(32 * sweep_warps(SHARE), 2) k_count_sweep(cons
         PairConst P;                                                   // setting-independent part (sigma fields overridden below)
         pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], 0.f, 0.f, 0.f, 0.f, 0.f);
         __syncwarp();
+        SATMC_ASSERT(n_cov >= 0 && n_cov <= kSweepMax && pair < p.n_pairs);
         for (int c = lane; c < n_cov; c += 32) {                       // per-setting constants, two settings per lane
             const float sx = __ldg(sigmas + 3 * c), sy = __ldg(sigmas + 3 * c + 1), st = __ldg(sigmas + 3 * c + 2);
             float ea, eb;
@@ -926,6 +927,7 @@ __device__ __forceinline__ unsigned poly_sample(const PolyPairShared& S, const P
     const unsigned mask = __ballot_sync(0xffffffffu, und);
     if (und) {
         const unsigned pos = fill + __popc(mask & ((1u << lane) - 1u));
+        SATMC_ASSERT(pos < kPolyQueueCap);
         Q.z[0][pos] = z0; Q.z[1][pos] = z1; Q.z[2][pos] = z2;
     }
     fill += __popc(mask);
@@ -1088,7 +1090,7 @@ __global__ void k_fused_normals(const __grid_constant__ PhiloxKeys K, uint32_t p
             const uint64_t s = 4 * g + t;
             if (s < offset || s >= offset + n) continue;
 #pragma unroll
-            for (int k = 0; k < D; k++) z[k * ldz + (s - offset)] = nn[D * t + k];
+            for (int k = 0; k < D; k++) { SATMC_ASSERT(s - offset < ldz); z[k * ldz + (s - offset)] = nn[D * t + k]; }
         }
     }
 }
@@ -1133,6 +1135,7 @@ __global__ void k_ztest_tail(const unsigned long long* __restrict__ hits, float*
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= num_left) return;
     const int e = live ? live[g] : g;
+    SATMC_ASSERT(e >= 0 && (live != nullptr || e < num_left));
     const int k = (int)cps[e] + (int)hits[g];
     const float slack = calc_slack(n_samples, k);
     const float p = (float)k / (float)n_samples;

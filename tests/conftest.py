@@ -13,6 +13,14 @@ if ROOT not in sys.path:
 PKG = "convex-2d-gpu-collision-detection_b200"
 
 
+def pytest_report_header(config):
+    try:
+        mod = importlib.import_module(PKG)
+        return f"libsatmc: {mod.load_library().satmc_version().decode()}  [{mod.LIB_PATH}]"
+    except Exception as e:                                    # the ABI tests report a missing library properly
+        return f"libsatmc: not loadable ({e})"
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
 

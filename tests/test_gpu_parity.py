@@ -296,6 +296,59 @@ def test_screening_equals_exact_on_4e10_samples(ctx, dev, workloads, satmc):
 
 
 # ---- sampler ------------------------------------------------------------------------------------------
+def extreme_pairs(satmc, n, seed, five=False):
+    """Pairs far outside the dataset prior: overall scale S log-uniform in [1e-6, 1e6], aspect ratios log-uniform up to 1e6
+    (extents clipped at 1e-6), robot placed at log-uniform multiples of the contact distance at a random bearing,
+    sd_x / sd_y log-uniform in [1e-4, 10] x the local scale, sd_theta log-uniform in [1e-4, 8] (8 sigma = the 64 rad guard of
+    the screening bound), headings anywhere in +-1e3 rad."""
+    rng = np.random.default_rng(seed)
+    lu = lambda lo, hi, k=n: np.exp(rng.uniform(np.log(lo), np.log(hi), k))
+    S = lu(1e-6, 1e6)
+    def extents():
+        a = lu(1.0, 1e6)
+        long_side = S * lu(0.1, 10.0)
+        short = np.maximum(long_side / a, 1e-6)
+        flip = rng.random(n) < 0.5
+        return np.where(flip, long_side, short), np.where(flip, short, long_side)
+    rw, rh = extents(); ow, oh = extents()
+    reach = 0.5 * (np.hypot(rw, rh) + np.hypot(ow, oh))
+    dist = reach * lu(1e-3, 3.0)
+    bearing = rng.uniform(0, 2 * np.pi, n)
+    local = np.minimum(np.minimum(rw, rh), np.minimum(ow, oh)) * lu(1.0, 1e3)      # between the thin side and the long side
+    sd_x, sd_y = local * lu(1e-4, 10.0), local * lu(1e-4, 10.0)
+    sd_t = lu(1e-4, 8.0)
+    sd_t[rng.random(n) < 0.1] = 0.0
+    rtheta = rng.uniform(-1e3, 1e3, n) * (rng.random(n) < 0.3) + rng.uniform(0, 2 * np.pi, n)
+    sd_w = np.where(rng.random(n) < 0.7, ow * lu(1e-4, 2.0), 0.0) if five else 0.0
+    sd_h = np.where(rng.random(n) < 0.7, oh * lu(1e-4, 2.0), 0.0) if five else 0.0
+    return satmc.pairs_from_columns(dist * np.cos(bearing), dist * np.sin(bearing), rtheta, ow, oh, sd_x, sd_y, sd_t, sd_w, sd_h, rw=rw, rh=rh)
+
+
+@pytest.mark.parametrize("five", [False, True])
+def test_screening_equals_exact_on_extreme_geometry(ctx, dev, satmc, five):
+    """Budgeted randomised search for a wrong screening decision where the terms M*dR/LA and eps_b/hmin of the bound dominate:
+    scales 1e-6 .. 1e6, aspect ratios to 1e6, sd_theta up to the guard.  Counts with the screening pass must equal the
+    all-exact evaluation pair by pair (6 x 50 000 pairs x 4 096 samples per variant = 1.2e9 tests, each evaluated twice)."""
+    n_pairs, n = 50_000, 4096
+    screened_total = undecided_total = 0
+    mixed = 0
+    for rep in range(6):
+        pairs = extreme_pairs(satmc, n_pairs, 9000 + rep + 100 * five, five)
+        ctx.exact_evals(reset=True)
+        fast = fused(ctx, dev, pairs, n, 31 + rep, sample_offset=rep * 1_000_003)
+        undecided_total += ctx.exact_evals(reset=True)
+        screened_total += n_pairs * n
+        exact = fused(ctx, dev, pairs, n, 31 + rep, sample_offset=rep * 1_000_003, flags=EXACT)
+        bad = np.nonzero(fast != exact)[0]
+        assert bad.size == 0, (rep, bad[:5], pairs[bad[:5]], fast[bad[:5]], exact[bad[:5]])
+        mixed += int(((exact > 0) & (exact < n)).sum())
+    # the search is only meaningful if the screening pass is what decides most samples and many pairs are near contact
+    assert undecided_total < 0.5 * screened_total, (undecided_total, screened_total)
+    assert mixed > 0.05 * 6 * n_pairs, mixed
+    print(f"extreme geometry ({'5' if five else '3'}-DoF): {screened_total:.3g} samples, {undecided_total / screened_total:.3%} went to the "
+          f"exact pass, {mixed} pairs with 0 < p < 1")
+
+
 def test_philox_kat_on_device(ctx, dev):
     from test_oracle import KAT
     for ctr, key, out in KAT:
