@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <new>
 
@@ -123,7 +124,6 @@ int satmc_create(int device, void* stream, satmc_ctx** out)
     cudaGetLastError();
     if (cudaMalloc(&ctx->d_exact_evals, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(ctx->d_exact_evals, 0, sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMalloc(&ctx->d_sweep_plan, sizeof(SweepPlan)) != cudaSuccess ||
         cudaMalloc(&ctx->d_ticket, 3 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(ctx->d_ticket, 0, 3 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_word, 64) != cudaSuccess ||
@@ -149,7 +149,6 @@ int satmc_destroy(satmc_ctx* ctx)
     for (int i = 0; i < 2; i++) if (ctx->d_acc[i]) cudaFree(ctx->d_acc[i]);
     if (ctx->d_exact_evals) cudaFree(ctx->d_exact_evals);
     if (ctx->d_ticket) cudaFree(ctx->d_ticket);
-    if (ctx->d_sweep_plan) cudaFree(ctx->d_sweep_plan);
     if (ctx->h_word) cudaFreeHost(ctx->h_word);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -211,8 +210,9 @@ int satmc_exact_evals(satmc_ctx* ctx, uint64_t* out, int reset)
 // REDUX warp total, the sweep's per-setting shared-memory counters), so no item may exceed 2^31 samples.
 constexpr uint64_t kMaxChunk = 1ull << 31;
 static int plan_items(satmc_ctx* ctx, CountParams& p, int bps, uint64_t& blocks, int items_per_warp = 8,
-                      uint64_t max_chunk = kMaxChunk)
+                      uint64_t max_chunk = kMaxChunk, int warps_per_block = kWarps)
 {
+    const uint64_t kWarps = (uint64_t)warps_per_block;                // (shadows the default block shape)
     const uint64_t resident_warps = (uint64_t)ctx->sm_count * bps * kWarps;
     const uint64_t target_items = resident_warps * (uint64_t)items_per_warp;
     const uint64_t min_chunk = ctx->tune_min_chunk;               // 64 samples per lane: amortises the pair prologue
@@ -260,7 +260,7 @@ extern "C" int satmc_plan_debug(satmc_ctx* ctx, int kind, uint64_t n_pairs, uint
     if (kind == 0) rc = plan_items(ctx, p, ctx->blocks_per_sm, blocks, 8, 1ull << 20);
     else if (kind == 1) rc = plan_items(ctx, p, ctx->blocks_per_sm_streamed, blocks);
     else if (kind == 2) rc = plan_items(ctx, p, 2, blocks);
-    else rc = plan_items(ctx, p, 2, blocks, 32);
+    else rc = plan_items(ctx, p, SATMC_SWEEP_BPS, blocks, 32, kMaxChunk, kSweepWarps);
     if (rc) return rc;
     *chunk_out = p.chunk; *n_chunks_out = p.n_chunks;
     return SATMC_OK;
@@ -569,27 +569,32 @@ int satmc_count_fused_sweep(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t 
     p.flags = flags;
     p.hits = reinterpret_cast<unsigned long long*>(d_hits); p.exact_evals = ctx->d_exact_evals;
     uint64_t blocks = 0;
-    int rc = plan_items(ctx, p, 2, blocks, 32);          // an item costs n_cov x a plain one: cut finer (+7 % on cfg5)
+    int rc = plan_items(ctx, p, SATMC_SWEEP_BPS, blocks, 32, kMaxChunk, kSweepWarps);   // an item costs n_cov x a plain one: cut finer (+7 % on cfg5)
     if (rc) return rc;
-    void* d_sig = nullptr;
-    rc = scratch(ctx, 2, 3 * (size_t)n_cov * sizeof(float), &d_sig);
-    if (rc) return rc;
-    CU(ctx, cudaMemcpyAsync(d_sig, h_sigmas, 3 * (size_t)n_cov * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    const float* d_sigmas = static_cast<const float*>(d_sig);
-    // settings are processed kSweepMax at a time; every slice sees the same normals
+    // settings are processed kSweepMax at a time; every slice sees the same normals.  Within a slice the settings are
+    // sorted by sd_theta (bit pattern; any total order will do) so that equal values are neighbours: the kernel keeps
+    // sine, cosine and the projected extents across them.
     for (uint32_t c0 = 0; c0 < n_cov; c0 += kSweepMax) {
         const int nc = (int)((n_cov - c0 < (uint32_t)kSweepMax) ? n_cov - c0 : kSweepMax);
+        SweepSettings W{};
+        W.n = nc;
+        int order[kSweepMax];
+        for (int i = 0; i < nc; i++) order[i] = i;
+        const float* sig = h_sigmas + 3 * (size_t)c0;
+        auto key = [&](int i) { uint32_t u; memcpy(&u, &sig[3 * i + 2], 4); return u; };
+        std::stable_sort(order, order + nc, [&](int x, int y) { return key(x) < key(y); });
+        for (int r = 0; r < nc; r++) {
+            const int i = order[r];
+            W.sx[r] = sig[3 * i]; W.sy[r] = sig[3 * i + 1]; W.st[r] = sig[3 * i + 2];
+            W.orig[r] = (unsigned char)i;
+        }
         CountParams q = p;
         q.hits = p.hits + c0;
         rc = prepare_counters(ctx, q, n_pairs * n_cov, n_pairs * (uint64_t)nc, (uint64_t)nc, (uint64_t)n_cov, c0);
         if (rc) return rc;
-        k_sweep_plan<<<1, kSweepMax, 0, ctx->stream>>>(d_sigmas + 3 * (size_t)c0, nc, ctx->d_sweep_plan);
-        k_count_sweep<false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(d_pairs, d_sigmas + 3 * (size_t)c0, nc, (uint64_t)n_cov, q,
-                                                                            ctx->d_sweep_plan);
-        k_count_sweep<true><<<(unsigned)blocks, 32 * sweep_warps(true), 0, ctx->stream>>>(d_pairs, d_sigmas + 3 * (size_t)c0, nc, (uint64_t)n_cov, q,
-                                                                           ctx->d_sweep_plan);
+        k_count_sweep<SATMC_SWEEP_G><<<(unsigned)blocks, 32 * kSweepWarps, 0, ctx->stream>>>(d_pairs, W, (uint64_t)n_cov, q);
         CU(ctx, cudaGetLastError());
-        ctx->launches += 3;
+        ctx->launches++;
     }
     return SATMC_OK;
 }

@@ -39,6 +39,27 @@ namespace satmc {
 #define SATMC_Z_BOUND 8.0f
 
 // ---------------------------------------------------------------------------------------------
+// packed FP32 (sm_100a FFMA2 / FMUL2 / FADD2: two IEEE round-to-nearest operations per instruction, lane by lane
+// identical to the scalar ones).  One packed instruction takes one issue slot for two FMA-pipe cycles, and -- unlike two
+// scalar FFMAs -- overlaps with the half-rate ALU-pipe instructions around it (tools/ubench.cu: 8 FFMA2 + 16 LOP3 take
+// 34 clk, 16 FFMA + 16 LOP3 take 45), which is what the screening loops are short of.
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 v; asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi)); return v; }
+__device__ __forceinline__ f32x2 dup2(float a) { return pack2(a, a); }
+__device__ __forceinline__ float lo2(f32x2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
+__device__ __forceinline__ float hi2(f32x2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// min(a, |b|, |c|) that returns NaN if any input is NaN (FMNMX3.NAN): a running minimum that cannot lose a NaN
+__device__ __forceinline__ float min3_nan_abs(float a, float b, float c)
+{
+    float d;
+    asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(fabsf(b)), "f"(fabsf(c)));
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------
 // exact reference arithmetic
 // ---------------------------------------------------------------------------------------------
 

@@ -7,9 +7,6 @@
 
 #include "../../include/satmc.h"
 
-namespace satmc { struct SweepPlan; }
-using satmc::SweepPlan;
-
 struct satmc_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -26,7 +23,6 @@ struct satmc_ctx {
     unsigned long long* d_ticket = nullptr;
     uint64_t ticket_next[2] = {0, 0};
     int ticket_sel = 0;
-    SweepPlan* d_sweep_plan = nullptr;       // written by k_sweep_plan, read by both k_count_sweep variants
     cudaStream_t aux = nullptr;              // pipelined host calls: second slice (created on first use)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool profiling = false;

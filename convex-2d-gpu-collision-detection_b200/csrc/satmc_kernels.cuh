@@ -660,136 +660,103 @@ k_count_streamed_tma(const __grid_constant__ DirectSrc src, const __grid_constan
 // Every pair is evaluated under n_cov pose-covariance settings (sd_x, sd_y, sd_theta) on the SAME normals: setting c
 // of pair p sees exactly the samples satmc_count_fused would give a pair with that sigma and stream id p.  The
 // sampler (47 % of the issue slots of the plain fused loop) is then paid once per sample instead of once per
-// (sample, setting): a lane draws two 4-sample groups (24 normals) and runs the 22-instruction screening test for all
-// settings from shared-memory constants.  Counts per setting are warp-reduced into shared memory.
+// (sample, setting): a lane draws two 4-sample groups (24 normals) and runs the screening test for all settings.
+//
+// The settings arrive as a launch parameter, sorted by sd_theta on the host (SweepSettings).  Settings with the same
+// sd_theta give every sample the same relative angle, hence the same sine and cosine AND the same four projected
+// extents (they depend on the angle and the box sizes only): the kernel recomputes those 2 MUFU + 9 FP32 per sample
+// only when sd_theta changes (a 4x4x4 grid: 4 times per 64 settings) and is left with 13 FP32 + 1 shift per
+// (sample, setting): two centre projections (4 FFMA), their rotation into the obstacle frame (1 FMUL + 2 FFMA + 1 FADD
+// folded), four gaps (4 FADD), the maximum (FMNMX3 x 2), the hit bit shifted into a per-lane mask (SHF) and the
+// "decided" predicate (FSETP).  Hits per setting are popcounted, warp-reduced and added to shared memory.
 // ---------------------------------------------------------------------------------------------
 constexpr int kSweepMax = 64;
 
+struct SweepSettings {                // by value in the kernel-parameter bank; order = ascending sd_theta bit pattern
+    float sx[kSweepMax], sy[kSweepMax], st[kSweepMax];
+    unsigned char orig[kSweepMax];    // sorted position -> position in the caller's array (the output column)
+    int n;
+};
+
+struct SweepSetting {             // 32 bytes: one pointer walks the settings, fields at immediate offsets
+    float4 k;                     // nkx0, nky0, kx1, nky1 of the pair under sorted setting r
+    float2 e;                     // nst, eps
+    unsigned cnt, pad;
+};
 struct SweepShared {
-    float4 k[kSweepMax];          // nkx0, nky0, kx1, nky1
-    float2 e[kSweepMax];          // nst, eps
-    float sig[kSweepMax][3];      // sd_x, sd_y, sd_theta (cold path)
-    unsigned cnt[kSweepMax];
+    SweepSetting s[kSweepMax];
     float robot[8];
     PairConst base;               // setting-independent constants, for the out-of-line paths
 };
 
 // one sample of one setting, screening + exact fallback (edges and undecided samples)
-__device__ __noinline__ unsigned sweep_sample_slow(const SweepShared& S, int c, float z0, float z1, float z2,
+__device__ __noinline__ unsigned sweep_sample_slow(const SweepShared& S, const SweepSettings& W, int r, float z0, float z1, float z2,
                                                    unsigned long long* exact_evals)
 {
     PairConst Q = S.base;
-    const float4 k = S.k[c]; const float2 e = S.e[c];
+    const float4 k = S.s[r].k; const float2 e = S.s[r].e;
     Q.nkx0 = k.x; Q.nky0 = k.y; Q.kx1 = k.z; Q.nky1 = k.w; Q.nst = e.x; Q.eps = e.y;
     float hmin;
     const float m = screen_gap<3>(Q, z0, z1, z2, 0.f, 0.f, hmin);
     unsigned hit = __float_as_uint(m) >> 31;
     if (!screen_decided<3>(Q, m, hmin)) {
-        hit = (unsigned)exact_decide(S.robot, Q.ow, Q.oh, S.sig[c][0], S.sig[c][1], S.sig[c][2], 0.f, 0.f, z0, z1, z2, 0.f, 0.f);
+        hit = (unsigned)exact_decide(S.robot, Q.ow, Q.oh, W.sx[r], W.sy[r], W.st[r], 0.f, 0.f, z0, z1, z2, 0.f, 0.f);
         if (exact_evals) atomicAdd(exact_evals, 1ull);
     }
     return hit;
 }
 
-// the 4 samples of group g for setting c, normals regenerated: rare path of the main loops
-__device__ __noinline__ unsigned sweep_group_slow(const SweepShared& S, int c, uint64_t g, uint32_t pid,
+// all samples of super-group q (groups G q .. G q + G - 1) for setting r, normals regenerated: rare path of the main loop
+__device__ __noinline__ unsigned sweep_super_slow(const SweepShared& S, const SweepSettings& W, int r, uint64_t q, int G, uint32_t pid,
                                                   const PhiloxKeys& K, unsigned long long* exact_evals)
 {
-    float n[12];
-    group_normals<3>((uint32_t)g, (uint32_t)(g >> 32), pid, K, n);
     unsigned cnt = 0;
-    for (int t = 0; t < 4; t++) cnt += sweep_sample_slow(S, c, n[3 * t], n[3 * t + 1], n[3 * t + 2], exact_evals);
+    for (int h = 0; h < G; h++) {
+        const uint64_t g = (uint64_t)G * q + h;
+        float n[12];
+        group_normals<3>((uint32_t)g, (uint32_t)(g >> 32), pid, K, n);
+        for (int t = 0; t < 4; t++) cnt += sweep_sample_slow(S, W, r, n[3 * t], n[3 * t + 1], n[3 * t + 2], exact_evals);
+    }
     return cnt;
 }
 
-// all 8 samples of super-group q (groups 2q, 2q+1)
-__device__ __noinline__ unsigned sweep_octet_slow(const SweepShared& S, int c, uint64_t q, uint32_t pid,
-                                                  const PhiloxKeys& K, unsigned long long* exact_evals)
+// the angle-dependent part of screen_gap_sc: the four projected extents (same arithmetic, same roundings)
+__device__ __forceinline__ void screen_extents(const PairConst& P, float s, float c, float& eb0, float& eb1, float& ea0, float& ea1)
 {
-    return sweep_group_slow(S, c, 2 * q, pid, K, exact_evals) + sweep_group_slow(S, c, 2 * q + 1, pid, K, exact_evals);
+    const float C = fabsf(c), S = fabsf(s);
+    eb0 = fmaf(P.a0, C, fmaf(P.a1, S, P.b0));
+    eb1 = fmaf(P.a0, S, fmaf(P.a1, C, P.b1));
+    ea0 = fmaf(P.b0, C, fmaf(P.b1, S, P.a0));
+    ea1 = fmaf(P.b0, S, fmaf(P.b1, C, P.a1));
 }
 
-// Settings that share sd_theta share the relative angle of every sample, hence sin and cos: the sweep visits the
-// settings in order of sd_theta (S.order) and recomputes the two MUFUs only when it changes (a 4x4x4 grid: 4 times
-// per 64 settings).  One 4-sample group per lane and trip, so that the kept sines and cosines fit in registers.
-__device__ __forceinline__ void sweep_trip_shared_theta(SweepShared& S, const unsigned char* order, const PairConst& P,
-                                                        const CountParams& p, int n_cov, uint64_t q, bool mine, uint32_t pid,
-                                                        unsigned long long* ev, int lane)
+// G = 4-sample groups per lane and trip (NS = 4 G samples); BPS = resident blocks per SM the register budget is cut for;
+// WARPS per block.  Measured on B200, cfg 5 (profiles/r2_sweep_experiments.log): 8 samples per trip in 6-warp blocks at
+// 168 registers (nothing spilled in the loop) 1027 Gtests/s; 4 samples in 8-warp blocks at 128 registers 958; 8 samples
+// at 128 registers (spills) 955; 8 samples at 232 registers, one block per SM 909.
+#ifndef SATMC_SWEEP_G
+#define SATMC_SWEEP_G 2
+#endif
+#ifndef SATMC_SWEEP_BPS
+#define SATMC_SWEEP_BPS 2
+#endif
+#ifndef SATMC_SWEEP_WARPS
+#define SATMC_SWEEP_WARPS 6
+#endif
+constexpr int kSweepWarps = SATMC_SWEEP_WARPS;
+template <int G>
+__global__ void __launch_bounds__(32 * kSweepWarps, SATMC_SWEEP_BPS) k_count_sweep(const satmc_pair* __restrict__ pairs, const __grid_constant__ SweepSettings W,
+                                                             uint64_t hits_stride, const __grid_constant__ CountParams p)
 {
-    float n[24];
-    group_normals<3>((uint32_t)(2 * q), (uint32_t)((2 * q) >> 32), pid, p.keys, n);
-    group_normals<3>((uint32_t)(2 * q + 1), (uint32_t)((2 * q + 1) >> 32), pid, p.keys, n + 12);
-    float sn[8], cs[8];
-    uint32_t have = 0u, prev = 0u;
-    for (int r = 0; r < n_cov; r++) {
-        const int c = order[r];
-        const float4 k = S.k[c]; const float2 ee = S.e[c];
-        if (!have || __float_as_uint(ee.x) != prev) {                  // warp-uniform: r and the tables are
-            prev = __float_as_uint(ee.x); have = 1u;
-#pragma unroll
-            for (int t = 0; t < 8; t++) screen_trig(ee.x, P.th, n[3 * t + 2], sn[t], cs[t]);
-        }
-        PairConst Q = P;
-        Q.nkx0 = k.x; Q.nky0 = k.y; Q.kx1 = k.z; Q.nky1 = k.w; Q.nst = ee.x; Q.eps = ee.y;
-        unsigned cnt = 0;
-        bool decided = true;
-#pragma unroll
-        for (int t = 0; t < 8; t++) {
-            float hmin;
-            const float m = screen_gap_sc<3>(Q, n[3 * t], n[3 * t + 1], sn[t], cs[t], 0.f, 0.f, hmin);
-            cnt += __float_as_uint(m) >> 31;
-            decided = decided && screen_decided<3>(Q, m, hmin);
-        }
-        if (!decided && mine) cnt = sweep_octet_slow(S, c, q, pid, p.keys, ev);
-        cnt = __reduce_add_sync(0xffffffffu, mine ? cnt : 0u);
-        if (lane == 0) S.cnt[c] += cnt;
-    }
-}
-
-// Per launch: the order of the settings by sd_theta (rank sort on the bit patterns; any total order will do) and whether
-// sharing pays -- at least half of the settings can reuse their predecessor's sine and cosine.  Both k_count_sweep
-// variants are launched; the one the plan does not select returns at once.
-struct SweepPlan {
-    int share_theta;
-    unsigned char order[kSweepMax];
-};
-
-__global__ void k_sweep_plan(const float* __restrict__ sigmas, int n_cov, SweepPlan* plan)
-{
-    const int c = threadIdx.x;
-    int first = 0;
-    if (c < n_cov) {
-        const uint32_t key = __float_as_uint(__ldg(sigmas + 3 * c + 2));
-        int rank = 0; first = 1;
-        for (int j = 0; j < n_cov; j++) {
-            const uint32_t kj = __float_as_uint(__ldg(sigmas + 3 * j + 2));
-            rank += (kj < key) || (kj == key && j < c);
-            first &= !(kj == key && j < c);
-        }
-        plan->order[rank] = (unsigned char)c;
-    }
-    const int runs = __syncthreads_count(first);
-    if (c == 0) plan->share_theta = (2 * runs <= n_cov) ? 1 : 0;
-}
-
-// (measured for SHARE, which keeps 8 sines and 8 cosines besides the 24 normals: 8 warps per block at 128 registers with
-// 21 spill instructions in the setting loop 791 Gtests/s; 6 warps at 168 registers, nothing spilled, 753)
-__host__ __device__ constexpr int sweep_warps(bool) { return kWarps; }
-
-template <bool SHARE>
-__global__ void __launch_bounds__(32 * sweep_warps(SHARE), 2) k_count_sweep(const satmc_pair* __restrict__ pairs, const float* __restrict__ sigmas,
-                                                             int n_cov, uint64_t hits_stride, const __grid_constant__ CountParams p,
-                                                             const SweepPlan* __restrict__ plan)
-{
-    if ((plan->share_theta != 0) != SHARE) return;
-    constexpr int W = sweep_warps(SHARE);
-    __shared__ SweepShared s_sw[W];
-    __shared__ unsigned char s_order[kSweepMax];
-    if (SHARE) { if (threadIdx.x < kSweepMax) s_order[threadIdx.x] = plan->order[threadIdx.x]; __syncthreads(); }
+    constexpr int NS = 4 * G;
+    constexpr int LG = (G == 1) ? 2 : 3;                              // log2(NS)
+    static_assert(G == 1 || G == 2, "one or two groups per trip");
+    __shared__ SweepShared s_sw[kSweepWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_cov = W.n;
     SweepShared& S = s_sw[warp];
-    const uint64_t stride = (uint64_t)gridDim.x * W;
-    for (uint64_t item = (uint64_t)blockIdx.x * W + warp; item < p.n_items; item += stride) {
+    const uint64_t stride = (uint64_t)gridDim.x * kSweepWarps;
+    for (uint64_t item = (uint64_t)blockIdx.x * kSweepWarps + warp; item < p.n_items; item += stride) {
         const uint64_t pair = item / p.n_chunks;
         const uint32_t chunk_id = (uint32_t)(item - pair * p.n_chunks);
         float v[12];
@@ -797,19 +764,18 @@ __global__ void __launch_bounds__(32 * sweep_warps(SHARE), 2) k_count_sweep(cons
         src.load(pair, v);
         PairConst P;                                                   // setting-independent part (sigma fields overridden below)
         pair_const_init(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], 0.f, 0.f, 0.f, 0.f, 0.f);
-        __syncwarp();
         SATMC_ASSERT(n_cov >= 0 && n_cov <= kSweepMax && pair < p.n_pairs);
-        for (int c = lane; c < n_cov; c += 32) {                       // per-setting constants, two settings per lane
-            const float sx = __ldg(sigmas + 3 * c), sy = __ldg(sigmas + 3 * c + 1), st = __ldg(sigmas + 3 * c + 2);
+        __syncwarp();
+        for (int r = lane; r < n_cov; r += 32) {                       // per-setting constants, two settings per lane
+            const float sx = W.sx[r], sy = W.sy[r], st = W.st[r];
             float ea, eb;
             screen_eps(v[0], v[1], v[2], P.a0, P.a1, P.b0, P.b1, sx, sy, st, 0.f, 0.f, ea, eb);
             const float hmin = fminf(P.b0, P.b1);
             const float e3 = ea + __fdividef(eb, hmin);
             const bool ok = hmin > 0.0f && e3 == e3 && !(p.flags & SATMC_EXACT_ONLY);
-            S.k[c] = make_float4(-(sx * P.ca), -(sy * P.sa), sx * P.sa, -(sy * P.ca));
-            S.e[c] = make_float2(-st, ok ? e3 : CUDART_INF_F);
-            S.sig[c][0] = sx; S.sig[c][1] = sy; S.sig[c][2] = st;
-            S.cnt[c] = 0;
+            S.s[r].k = make_float4(-(sx * P.ca), -(sy * P.sa), sx * P.sa, -(sy * P.ca));
+            S.s[r].e = make_float2(-st, ok ? e3 : CUDART_INF_F);
+            S.s[r].cnt = 0;
         }
         if (lane == 0) {
             float base[8];
@@ -823,42 +789,82 @@ __global__ void __launch_bounds__(32 * sweep_warps(SHARE), 2) k_count_sweep(cons
         unsigned long long* ev = (p.flags & SATMC_EXACT_ONLY) ? nullptr : p.exact_evals;
         const uint32_t pid = p.pair_id_offset + (uint32_t)pair;
         const uint64_t b = p.sample_offset + c_begin, e = b + c_len;
-        const uint64_t q_lo = (b + 7) >> 3, q_hi = e >> 3;              // full 8-sample super-groups [q_lo, q_hi)
-        if (SHARE && q_lo <= q_hi) {
-            for (uint64_t q0 = q_lo; q0 < q_hi; q0 += 32) {
-                const uint64_t q = q0 + (uint64_t)lane;
-                sweep_trip_shared_theta(S, s_order, P, p, n_cov, q, q < q_hi, pid, ev, lane);
-            }
-        } else if (q_lo <= q_hi) {
-            for (uint64_t q0 = q_lo; q0 < q_hi; q0 += 32) {             // all 32 lanes stay in step; idle lanes count nothing
-                const uint64_t q = q0 + (uint64_t)lane;
-                const bool mine = q < q_hi;
-                float n[24];
-                group_normals<3>((uint32_t)(2 * q), (uint32_t)((2 * q) >> 32), pid, p.keys, n);
-                group_normals<3>((uint32_t)(2 * q + 1), (uint32_t)((2 * q + 1) >> 32), pid, p.keys, n + 12);
-                for (int c = 0; c < n_cov; c++) {
-                    const float4 k = S.k[c]; const float2 ee = S.e[c];
-                    PairConst Q = P;
-                    Q.nkx0 = k.x; Q.nky0 = k.y; Q.kx1 = k.z; Q.nky1 = k.w; Q.nst = ee.x; Q.eps = ee.y;
-                    unsigned cnt = 0;
-                    bool decided = true;
+        const uint64_t q_lo = (b + NS - 1) >> LG, q_hi = e >> LG;       // full NS-sample super-groups [q_lo, q_hi)
+        for (uint64_t q0 = q_lo; q0 < q_hi; q0 += 32) {                 // all 32 lanes stay in step; idle lanes count nothing
+            const uint64_t q = q0 + (uint64_t)lane;
+            const bool mine = q < q_hi;
+            float n[3 * NS];
 #pragma unroll
-                    for (int t = 0; t < 8; t++) {
-                        float hmin;
-                        const float m = screen_gap<3>(Q, n[3 * t], n[3 * t + 1], n[3 * t + 2], 0.f, 0.f, hmin);
-                        cnt += __float_as_uint(m) >> 31;
-                        decided = decided && screen_decided<3>(Q, m, hmin);
-                    }
-                    if (!decided && mine) cnt = sweep_octet_slow(S, c, q, pid, p.keys, ev);
-                    cnt = __reduce_add_sync(0xffffffffu, mine ? cnt : 0u);
-                    if (lane == 0) S.cnt[c] += cnt;
-                }
+            for (int h = 0; h < G; h++) {
+                const uint64_t g = (uint64_t)G * q + h;
+                group_normals<3>((uint32_t)g, (uint32_t)(g >> 32), pid, p.keys, n + 12 * h);
             }
+            // samples in pairs (2j, 2j+1): the centre projections and their rotation run as packed FP32
+            f32x2 z0p[NS / 2], z1p[NS / 2], cs2[NS / 2], sn2[NS / 2], ns2[NS / 2];
+            float eb0[NS], eb1[NS], ea0[NS], ea1[NS];
+#pragma unroll
+            for (int j = 0; j < NS / 2; j++) { z0p[j] = pack2(n[6 * j], n[6 * j + 3]); z1p[j] = pack2(n[6 * j + 1], n[6 * j + 4]); }
+            const f32x2 pa0_2 = dup2(P.pa0), pa1_2 = dup2(P.pa1);
+            unsigned mine_mask = mine ? 0xffffffffu : 0u;
+            asm volatile("" : "+r"(mine_mask));                          // keep it in a register (else it is re-derived per setting)
+            unsigned long long und = 0ull;
+            uint32_t prev = 0u;
+            SweepSetting* sp = S.s;
+            for (int r = 0; r < n_cov; r++, sp++) {
+                const float4 k = sp->k; const float2 ee = sp->e;
+                if (r == 0 || __float_as_uint(ee.x) != prev) {           // warp-uniform: sd_theta changes (sorted: once per value)
+                    prev = __float_as_uint(ee.x);
+#pragma unroll
+                    for (int j = 0; j < NS / 2; j++) {
+                        float s0, c0, s1, c1;
+                        screen_trig(ee.x, P.th, n[6 * j + 2], s0, c0);
+                        screen_trig(ee.x, P.th, n[6 * j + 5], s1, c1);
+                        screen_extents(P, s0, c0, eb0[2 * j], eb1[2 * j], ea0[2 * j], ea1[2 * j]);
+                        screen_extents(P, s1, c1, eb0[2 * j + 1], eb1[2 * j + 1], ea0[2 * j + 1], ea1[2 * j + 1]);
+                        cs2[j] = pack2(c0, c1); sn2[j] = pack2(s0, s1); ns2[j] = pack2(-s0, -s1);
+                    }
+                }
+                const f32x2 kx = dup2(k.x), ky = dup2(k.y), kz = dup2(k.z), kw = dup2(k.w);
+                unsigned hits = 0u;
+                float mn = CUDART_INF_F;                                 // min |m| over the samples (NaN-propagating)
+#pragma unroll
+                for (int j = 0; j < NS / 2; j++) {
+                    const f32x2 ua0 = fma2(kx, z0p[j], fma2(ky, z1p[j], pa0_2));
+                    const f32x2 ua1 = fma2(kz, z0p[j], fma2(kw, z1p[j], pa1_2));
+                    const f32x2 ub0 = fma2(cs2[j], ua0, mul2(ns2[j], ua1));
+                    const f32x2 ub1 = fma2(sn2[j], ua0, mul2(cs2[j], ua1));
+                    const float m0 = fmaxf(fmaxf(fabsf(lo2(ub0)) - eb0[2 * j], fabsf(lo2(ub1)) - eb1[2 * j]),
+                                           fmaxf(fabsf(lo2(ua0)) - ea0[2 * j], fabsf(lo2(ua1)) - ea1[2 * j]));
+                    const float m1 = fmaxf(fmaxf(fabsf(hi2(ub0)) - eb0[2 * j + 1], fabsf(hi2(ub1)) - eb1[2 * j + 1]),
+                                           fmaxf(fabsf(hi2(ua0)) - ea0[2 * j + 1], fabsf(hi2(ua1)) - ea1[2 * j + 1]));
+                    hits += __float_as_uint(m0) >> 31;                      // sign bit of m = hit (m = -0 / NaN are undecided anyway)
+                    hits += __float_as_uint(m1) >> 31;
+                    mn = min3_nan_abs(mn, m0, m1);
+                }
+                // A lane with an undecided sample (also NaN) under this setting contributes a marker instead of its hits; its
+                // samples are redone exactly after the loop.  The marker surfaces in the warp total, so the bookkeeping sits
+                // behind a branch on a warp-uniform value that is taken about once in 200 iterations.
+                const bool decided = mn > ee.y;
+                const unsigned tot = __reduce_add_sync(0xffffffffu, decided ? (hits & mine_mask) : (mine_mask & 0x10000u));
+                if (tot >= 0x10000u) {
+                    const unsigned who = __ballot_sync(0xffffffffu, !decided && mine_mask != 0u);
+                    if ((who >> lane) & 1u) und |= 1ull << r;
+                }
+                sp->cnt += tot & 0xffffu;                                // every lane writes the same value: no branch, no atomic
+            }
+            // rare: this lane's samples under the settings that had an undecided one, exactly (kept out of the loop above so
+            // that the loop contains no call: with one, ptxas keeps the per-sample state in local memory)
+            __syncwarp();
+            if (mine && und != 0ull) {
+                for (int r = 0; r < n_cov; r++)
+                    if ((und >> r) & 1ull) atomicAdd(&S.s[r].cnt, sweep_super_slow(S, W, r, q, G, pid, p.keys, ev));
+            }
+            __syncwarp();
         }
         __syncwarp();
         // ragged ends: samples of [b, e) outside the full super-groups; lanes parallelise over settings
-        const uint64_t head_end = (q_lo <= q_hi) ? ((q_lo << 3) < e ? (q_lo << 3) : e) : e;
-        const uint64_t tail_begin = (q_lo <= q_hi) ? (q_hi << 3) : e;
+        const uint64_t head_end = (q_lo <= q_hi) ? ((q_lo << LG) < e ? (q_lo << LG) : e) : e;
+        const uint64_t tail_begin = (q_lo <= q_hi) ? (q_hi << LG) : e;
         for (int part = 0; part < 2; part++) {
             const uint64_t lo = part ? (tail_begin > head_end ? tail_begin : head_end) : b;
             const uint64_t hi = part ? e : head_end;
@@ -870,18 +876,18 @@ __global__ void __launch_bounds__(32 * sweep_warps(SHARE), 2) k_count_sweep(cons
                 if (t == 1) { z0 = n[3]; z1 = n[4]; z2 = n[5]; }
                 if (t == 2) { z0 = n[6]; z1 = n[7]; z2 = n[8]; }
                 if (t == 3) { z0 = n[9]; z1 = n[10]; z2 = n[11]; }
-                for (int c = lane; c < n_cov; c += 32) S.cnt[c] += sweep_sample_slow(S, c, z0, z1, z2, ev);
+                for (int r = lane; r < n_cov; r += 32) S.s[r].cnt += sweep_sample_slow(S, W, r, z0, z1, z2, ev);
             }
         }
         __syncwarp();
-        for (int c = lane; c < n_cov; c += 32) {
-            const unsigned long long tot = S.cnt[c];
-            SATMC_ASSERT(pair * hits_stride + c < p.hits_len);
+        for (int r = lane; r < n_cov; r += 32) {
+            const unsigned long long tot = S.s[r].cnt;
+            const uint64_t off = pair * hits_stride + (uint64_t)W.orig[r];
+            SATMC_ASSERT(off < p.hits_len);
             if (p.n_chunks == 1) {
-                unsigned long long* dst = p.hits + pair * hits_stride + c;
-                if (p.flags & SATMC_ACCUMULATE) *dst += tot; else *dst = tot;
+                if (p.flags & SATMC_ACCUMULATE) p.hits[off] += tot; else p.hits[off] = tot;
             } else {
-                atomicAdd(counter_base(p) + pair * hits_stride + c, tot);
+                atomicAdd(counter_base(p) + off, tot);
             }
         }
         __syncwarp();

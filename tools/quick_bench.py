@@ -39,6 +39,8 @@ def main():
     ctx = satmc.Context(0, torch.cuda.current_stream().cuda_stream)
     print(torch.cuda.get_device_name(0))
     flags = [0] + ([satmc.SATMC_EXACT_ONLY] if "--exact" in sys.argv else [])
+    if "--only" in sys.argv:
+        return rest_part(ctx)
     cases = (("cfg3 1e5x1e4", wl.dataset_pairs(100_000, 3), 10_000),
                            ("cfg3 5dof 1e5x1e4", wl.dataset_pairs(100_000, 3, shape_variance=True), 10_000),
                            ("cfg5 slice 64000x1e5", wl.variance_sweep_pairs(1000, 5), 100_000),
@@ -58,8 +60,12 @@ def main():
             tests = pairs.size * n
             print(f"fused  {name:24s} flags={fl} best {best:9.3f} ms  med {med:9.3f} ms  {tests / best / 1e6:10.2f} Gtests/s "
                   f" exact-eval frac {ev / (tests * (3 + 2 + 7 if pairs.size * n <= 5e9 else 2 + 3)):.2e}  p={d_hits.sum().item() / tests:.4f}")
-    if "--short" in sys.argv and "--streamed" not in sys.argv:
-        return
+    if "--short" not in sys.argv or "--streamed" in sys.argv:
+        streamed_part(ctx)
+    rest_part(ctx)
+
+
+def streamed_part(ctx):
     # streamed: shared L2-resident bank (cfg5) and HBM-bound private slices
     pairs = wl.variance_sweep_pairs(1000, 5)
     d_pairs = put(pairs); d_hits = torch.zeros(pairs.size, dtype=torch.int64, device="cuda")
@@ -76,6 +82,9 @@ def main():
         gb = ndof * 4 * npairs * n / 1e9
         print(f"streamed private ndof={ndof} {npairs}x{n}: best {best:.3f} ms {npairs * n / best / 1e6:.2f} Gtests/s  {gb / best * 1e3:.1f} GB/s")
         del z
+
+
+def rest_part(ctx):
     if "--sweep" in sys.argv:
         base = wl.dataset_pairs(10_000, 5)
         grid = np.array([0.01, 0.05, 0.15, 0.3]); vx, vy, vt = np.meshgrid(grid, grid, grid, indexing="ij")

@@ -61,6 +61,12 @@ __global__ void __launch_bounds__(1024, 1) k(uint32_t seed, uint32_t* sink, long
             if (OP == 24) { f[i] = fmaf(f[i], f[(i + 1) % ILP], f[(i + 3) % ILP]); }                                         // FFMA, three register sources
             if (OP == 25) { f[i] = fmaf(f[i], f[(i + 1) % ILP], 1e-9f); }                                                   // FFMA, two register sources
             if (OP == 26) { f[i] = fmaf(f[(i + 2) % ILP], f[(i + 1) % ILP], f[(i + 3) % ILP]) + f[i] * 1e-9f; }              // FFMA 3 regs (dst != src) + FFMA
+            if (OP == 30) { unsigned long long x = ((unsigned long long)__float_as_uint(f[(i + 1) % ILP]) << 32) | __float_as_uint(f[i]);      // FFMA2 (packed 2 x FP32)
+                            asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x) : "l"(0x3f8000013f800001ull), "l"(0x3089705f3089705full));
+                            f[i] = __uint_as_float((unsigned)x); }
+            if (OP == 31) { f[i] = fmaxf(fmaxf(f[i], f[(i + 1) % ILP]), f[(i + 3) % ILP]) * 1.0000001f; }                        // FMNMX3 + FMUL
+            if (OP == 32) { a[i] = __funnelshift_l(__float_as_uint(f[i]), a[i], 1); }                                           // SHF
+            if (OP == 33) { a[i] += (fabsf(f[i]) > f[(i + 1) % ILP]) ? 1u : 0u; }                                               // FSETP + predicated add
             if (OP == 16) { a[i] = __float_as_uint(f[i] = fmaf(f[i], 1.0000001f, 1e-9f)) >> 31; }                           // FFMA + SHF
         }
     }
@@ -73,6 +79,52 @@ __global__ void __launch_bounds__(1024, 1) k(uint32_t seed, uint32_t* sink, long
 }
 
 static int g_threads = 1024;
+
+// packed FP32 (fma.rn.f32x2 -> FFMA2 on sm_100a): 8 independent 64-bit accumulators per thread
+template <int OP>
+__global__ void __launch_bounds__(1024, 1) k2(uint32_t seed, uint32_t* sink, long long* cyc)
+{
+    unsigned long long x[8]; float f[16]; uint32_t a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { x[i] = 0x3f8000003f800000ull + seed + threadIdx.x * 7u + i; a[i] = seed + i * 77u + threadIdx.x; }
+#pragma unroll
+    for (int i = 0; i < 16; i++) f[i] = 1.0f + (float)((seed + i * 13u + threadIdx.x) & 1023) * 1e-3f;
+    const unsigned long long m = 0x3f8000013f800001ull, c = 0x3089705f3089705full;
+    __syncthreads();
+    long long t0 = clock64();
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (OP == 0 || OP == 2) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[i]) : "l"(m), "l"(c));
+            if (OP == 1 || OP == 3) { f[2 * i] = fmaf(f[2 * i], 1.0000001f, 1e-9f); f[2 * i + 1] = fmaf(f[2 * i + 1], 1.0000001f, 1e-9f); }
+            if (OP == 2 || OP == 3) a[i] = (a[i] ^ seed) & (a[(i + 1) % 8] | 0x55u);
+            if (OP == 4) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(x[i]) : "l"(c));
+            if (OP == 5) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(x[i]) : "l"(m));
+        }
+    }
+    long long t1 = clock64();
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += (uint32_t)x[i] + (uint32_t)(x[i] >> 32) + a[i] + __float_as_uint(f[2 * i]) + __float_as_uint(f[2 * i + 1]);
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int OP> void run2(const char* name, int instr_per_iter)
+{
+    int sms = 148;
+    uint32_t* sink; long long* cyc;
+    cudaMalloc(&sink, sms * 1024 * 4); cudaMalloc(&cyc, sms * 8);
+    k2<OP><<<sms, 1024>>>(12345u, sink, cyc);
+    k2<OP><<<sms, 1024>>>(12345u, sink, cyc);
+    cudaDeviceSynchronize();
+    long long h[148]; cudaMemcpy(h, cyc, sms * 8, cudaMemcpyDeviceToHost);
+    double avg = 0; for (int i = 0; i < sms; i++) avg += h[i]; avg /= sms;
+    const double warps_per_smsp = 8.0;
+    printf("%-28s %8.1f cyc  %6.3f clk per SMSP per iteration (%d warp-instr): %5.3f warp-instr/clk/SMSP\n", name, avg,
+           avg / ITERS / warps_per_smsp, instr_per_iter, instr_per_iter * ITERS * warps_per_smsp / avg);
+    cudaFree(sink); cudaFree(cyc);
+}
 
 template <int OP> void run(const char* name, int instr_per_op)
 {
@@ -92,6 +144,12 @@ template <int OP> void run(const char* name, int instr_per_op)
 
 int main(int argc, char** argv)
 {
+    if (argc > 3) {                      // packed FP32 and the ALU-pipe instructions of the sweep loop
+        run2<0>("FFMA2 x8 (16 FMA)", 8); run2<1>("FFMA x16", 16); run2<2>("FFMA2 x8 + LOP3 x8", 16); run2<3>("FFMA x16 + LOP3 x8", 24);
+        run2<4>("FADD2 x8", 8); run2<5>("FMUL2 x8", 8);
+        run<31>("FMNMX3+FMUL", 2); run<32>("SHF", 1); run<33>("FSETP+IADD", 2);
+        return 0;
+    }
     if (argc > 2) {                      // register-operand probe
         run<3>("FFMA r,imm,imm", 1); run<25>("FFMA r,r,imm", 1); run<24>("FFMA r,r,r", 1); run<26>("FFMA r,r,r + FFMA r,imm,r", 2);
         return 0;
