@@ -903,33 +903,81 @@ __global__ void __launch_bounds__(32 * kSweepWarps, SATMC_SWEEP_BPS) k_count_swe
 // exact SAT for the rest lane by lane would leave the warp mostly idle.  Samples are appended with a ballot (warp-
 // uniform fill count) and evaluated 32 at a time with all lanes busy -- by ONE copy of the exact code per vertex-count
 // variant (poly_queue_drain), called once per trip of the sample loop.
-constexpr unsigned kPolyQueueCap = 160;                               // 31 left over + 4 x 32 appended per trip
-struct PolyQueue { float z[3][kPolyQueueCap]; };
+// The first-level queue is drained when it holds kPolyDrainAt samples: several passes per (out-of-line) call, and the
+// sample loop itself contains no call (with one, ptxas keeps the loop's state in local memory: 130-190 spill
+// instructions per trip).  Capacity = what is left below the threshold + 4 x 32 appended by one more trip.
+constexpr unsigned kPolyDrainAt = 160;
+constexpr unsigned kPolyQueueCap = kPolyDrainAt - 1 + 128 + 1;
+constexpr unsigned kPolyQueue2Cap = 64;                               // second level: 31 left over + 32 appended per pass
+struct PolyQueue { float z[3][kPolyQueueCap]; float y[3][kPolyQueue2Cap]; };
 
-// evaluates queued samples from the top of the queue, 32 at a time; with `all` also the last, partly filled pass
-template <int NR, int NO>
-__device__ __forceinline__ unsigned poly_queue_drain(const PolyPairShared& S, const PolyRobotRegs& R, PolyQueue& Q, unsigned& fill,
-                                                     bool all, int lane, unsigned long long* exact_evals)
+// The exact polygon SAT of one sample: ONE out-of-line copy with run-time vertex counts (about 1 % of the samples get
+// here; the straight-line variants of round 1 made the kernel 27 000 instructions long and the hot loop miss the
+// instruction cache).
+__device__ __noinline__ unsigned poly_exact_sample(const PolyPairShared& S, float z0, float z1, float z2)
 {
+    PolyRobotRegs R;
+    poly_load_robot(S, R);
+    return poly_collide<0, 0>(S, R, z0, z1, z2);
+}
+
+// Second level (poly_fast) on the samples the circle tests left open, 32 at a time with all lanes busy; the few it cannot
+// decide either (|G| within the rounding bound of the true gap) move on to a second queue for the exact pass.  Out of
+// line: one copy per vertex-count variant, and the sample loop's registers are not shared with it.  Returns the hits;
+// fill / fill2 (warp-uniform) travel packed in `state` = fill | fill2 << 16.
+template <int NR, int NO>
+__device__ __noinline__ unsigned poly_queue_drain_fast(const PolyPairShared& S, PolyQueue& Q, unsigned& state, bool all, int lane,
+                                                       unsigned long long* exact_evals)
+{
+    PolyRobotRegs R;
+    poly_load_robot(S, R);
+    unsigned fill = state & 0xffffu, fill2 = state >> 16;
     unsigned hit = 0;
     __syncwarp();
     while (fill >= 32u || (all && fill > 0u)) {
         const unsigned n = fill < 32u ? fill : 32u;
         fill -= n;
-        if ((unsigned)lane < n) hit += poly_collide<NR, NO>(S, R, Q.z[0][fill + lane], Q.z[1][fill + lane], Q.z[2][fill + lane]);
-        if (exact_evals && lane == 0) atomicAdd(exact_evals, (unsigned long long)n);
+        const bool mine = (unsigned)lane < n;
+        float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+        int r = 1;
+        if (mine) {
+            z0 = Q.z[0][fill + lane]; z1 = Q.z[1][fill + lane]; z2 = Q.z[2][fill + lane];
+            r = poly_fast<NR, NO>(S, R, z0, z1, z2);
+        }
+        hit += (r == 2) ? 1u : 0u;
+        const bool und = mine && r == 0;
+        const unsigned mask = __ballot_sync(0xffffffffu, und);
+        if (und) {
+            const unsigned pos = fill2 + __popc(mask & ((1u << lane) - 1u));
+            SATMC_ASSERT(pos < kPolyQueue2Cap);
+            Q.y[0][pos] = z0; Q.y[1][pos] = z1; Q.y[2][pos] = z2;
+        }
+        fill2 += __popc(mask);
+        __syncwarp();
+        if (fill2 >= 32u) {                                             // a full pass of the exact SAT
+            fill2 -= 32u;
+            hit += poly_exact_sample(S, Q.y[0][fill2 + lane], Q.y[1][fill2 + lane], Q.y[2][fill2 + lane]);
+            if (exact_evals && lane == 0) atomicAdd(exact_evals, 32ull);
+            __syncwarp();
+        }
+    }
+    if (all && fill2 > 0u) {
+        if ((unsigned)lane < fill2) hit += poly_exact_sample(S, Q.y[0][lane], Q.y[1][lane], Q.y[2][lane]);
+        if (exact_evals && lane == 0) atomicAdd(exact_evals, (unsigned long long)fill2);
+        fill2 = 0u;
     }
     __syncwarp();
+    state = fill | (fill2 << 16);
     return hit;
 }
 
-// one sample through the screening pass; undecided ones are queued.  `fill` is warp-uniform.
-template <int NR>
+// one sample through the first screening level; undecided ones are queued.  `fill` is warp-uniform.
+template <int NR, bool RANGE>
 __device__ __forceinline__ unsigned poly_sample(const PolyPairShared& S, const PolyScreenRegs<NR>& C, PolyQueue& Q, unsigned& fill,
-                                                bool valid, bool screen, float z0, float z1, float z2, int lane)
+                                                bool valid, float z0, float z1, float z2, int lane)
 {
-    const int r = (valid && screen) ? poly_screen<NR>(S, C, z0, z1, z2) : 0;
-    const bool und = valid && r == 0;
+    const int r = valid ? poly_screen<NR, RANGE>(S, C, z0, z1, z2) : 1;
+    const bool und = r == 0;
     const unsigned mask = __ballot_sync(0xffffffffu, und);
     if (und) {
         const unsigned pos = fill + __popc(mask & ((1u << lane) - 1u));
@@ -937,45 +985,72 @@ __device__ __forceinline__ unsigned poly_sample(const PolyPairShared& S, const P
         Q.z[0][pos] = z0; Q.z[1][pos] = z1; Q.z[2][pos] = z2;
     }
     fill += __popc(mask);
-    return (r == 2) ? 1u : 0u;
+    return (valid && r == 2) ? 1u : 0u;
 }
 
-// samples of one work item; NR, NO as in poly_collide.  All 32 lanes walk the loops in step (ballots inside).
-template <int NR, int NO, bool STREAMED>
-__device__ __forceinline__ unsigned poly_chunk(const PolyPairShared& S, const PolyRobotRegs& R, PolyQueue& Q, const CountParams& p,
+// the second level, one out-of-line copy per vertex-count variant
+__device__ __forceinline__ unsigned poly_drain(const PolyPairShared& S, PolyQueue& Q, unsigned& fill, unsigned& fill2, bool all, int lane,
+                                               unsigned long long* ev)
+{
+    unsigned state = fill | (fill2 << 16);                              // both warp-uniform
+    const int shape = (S.nr == S.no) ? S.nr : 0;
+    unsigned h;
+    if (shape == 4) h = poly_queue_drain_fast<4, 4>(S, Q, state, all, lane, ev);
+    else if (shape == 3) h = poly_queue_drain_fast<3, 3>(S, Q, state, all, lane, ev);
+    else if (shape == 6) h = poly_queue_drain_fast<6, 6>(S, Q, state, all, lane, ev);
+    else if (shape == 8) h = poly_queue_drain_fast<8, 8>(S, Q, state, all, lane, ev);
+    else h = poly_queue_drain_fast<0, 0>(S, Q, state, all, lane, ev);
+    fill = state & 0xffffu; fill2 = state >> 16;
+    return h;
+}
+
+// samples of one work item; NR = robot vertex count known at compile time (0: read from S).  All 32 lanes walk the loops
+// in step (ballots inside).
+template <int NR, bool STREAMED>
+__device__ __forceinline__ unsigned poly_chunk(const PolyPairShared& S, PolyQueue& Q, const CountParams& p,
                                                uint64_t pair, uint64_t c_begin, uint64_t c_len, int lane)
 {
-    unsigned cnt = 0, fill = 0;
+    unsigned cnt = 0, fill = 0, fill2 = 0;
     PolyScreenRegs<NR> C;
     poly_load_screen<NR>(S, C);
-    const bool screen = !(p.flags & SATMC_EXACT_ONLY);
-    unsigned long long* ev = screen ? p.exact_evals : nullptr;
+    unsigned long long* ev = (p.flags & SATMC_EXACT_ONLY) ? nullptr : p.exact_evals;
     if (STREAMED) {
         const float* z = p.z + pair * p.z_pair_stride + c_begin;
-        for (uint64_t i0 = 0; i0 < c_len; i0 += 32) {
-            const uint64_t i = i0 + (uint64_t)lane;
-            const bool valid = i < c_len;
-            const float z0 = valid ? __ldg(z + i) : 0.f, z1 = valid ? __ldg(z + p.ldz + i) : 0.f, z2 = valid ? __ldg(z + 2 * p.ldz + i) : 0.f;
-            cnt += poly_sample<NR>(S, C, Q, fill, valid, screen, z0, z1, z2, lane);
-            if (fill >= 32u) cnt += poly_queue_drain<NR, NO>(S, R, Q, fill, false, lane, ev);
+        uint64_t i0 = 0;
+        while (i0 < c_len) {
+            for (; i0 < c_len && fill < kPolyDrainAt; i0 += 32) {         // call-free inner loop
+                const uint64_t i = i0 + (uint64_t)lane;
+                const bool valid = i < c_len;
+                const float z0 = valid ? __ldg(z + i) : 0.f, z1 = valid ? __ldg(z + p.ldz + i) : 0.f, z2 = valid ? __ldg(z + 2 * p.ldz + i) : 0.f;
+                cnt += poly_sample<NR, true>(S, C, Q, fill, valid, z0, z1, z2, lane);
+            }
+            if (fill >= kPolyDrainAt) cnt += poly_drain(S, Q, fill, fill2, false, lane, ev);
         }
     } else {
         const uint32_t pid = p.pair_id_offset + (uint32_t)pair;
         const uint64_t b = p.sample_offset + c_begin, e = b + c_len;
         const uint64_t g_end = (e + 3) >> 2;
-        for (uint64_t g0 = b >> 2; g0 < g_end; g0 += 32) {               // 4-sample groups, ragged ends masked
-            const uint64_t g = g0 + (uint64_t)lane;
-            float n[12];
-            group_normals<3>((uint32_t)g, (uint32_t)(g >> 32), pid, p.keys, n);
+        uint64_t g0 = b >> 2;
+        while (g0 < g_end) {
+            for (; g0 < g_end && fill < kPolyDrainAt; g0 += 32) {         // 4-sample groups; call-free inner loop
+                const uint64_t g = g0 + (uint64_t)lane;
+                float n[12];
+                group_normals<3>((uint32_t)g, (uint32_t)(g >> 32), pid, p.keys, n);
+                if (4 * g0 >= b && 4 * (g0 + 31) + 3 < e) {              // warp-uniform: every sample of the trip is inside [b, e)
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const uint64_t sidx = 4 * g + t;
-                cnt += poly_sample<NR>(S, C, Q, fill, sidx >= b && sidx < e, screen, n[3 * t], n[3 * t + 1], n[3 * t + 2], lane);
+                    for (int t = 0; t < 4; t++) cnt += poly_sample<NR, false>(S, C, Q, fill, true, n[3 * t], n[3 * t + 1], n[3 * t + 2], lane);
+                } else {                                                // ragged ends masked
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const uint64_t sidx = 4 * g + t;
+                        cnt += poly_sample<NR, false>(S, C, Q, fill, sidx >= b && sidx < e, n[3 * t], n[3 * t + 1], n[3 * t + 2], lane);
+                    }
+                }
             }
-            if (fill >= 32u) cnt += poly_queue_drain<NR, NO>(S, R, Q, fill, false, lane, ev);
+            if (fill >= kPolyDrainAt) cnt += poly_drain(S, Q, fill, fill2, false, lane, ev);
         }
     }
-    cnt += poly_queue_drain<NR, NO>(S, R, Q, fill, true, lane, ev);
+    cnt += poly_drain(S, Q, fill, fill2, true, lane, ev);
     return cnt;
 }
 
@@ -994,22 +1069,21 @@ __global__ void __launch_bounds__(kThreads, 2) k_count_poly(const float* __restr
         SATMC_ASSERT(pair < p.hits_len);
         __syncwarp();
         if (lane == 0) {
-            poly_prologue(s_poly[warp], pairs + pair * 40);                        // 160-byte descriptors
+            const float* d = pairs + pair * 40;                                   // 160-byte descriptors
+            poly_prologue(s_poly[warp], d);
             poly_screen_prologue(s_poly[warp], !(p.flags & SATMC_EXACT_ONLY));
+            poly_fast_prologue(s_poly[warp], d[0], d[1], d + 8, !(p.flags & SATMC_EXACT_ONLY));
         }
         __syncwarp();
         const PolyPairShared& S = s_poly[warp];
-        PolyRobotRegs R;
-        poly_load_robot(S, R);
         const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
         const uint64_t c_len = (c_begin + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - c_begin);
-        unsigned cnt;                                                  // straight-line code for the common equal vertex counts
-        const int shape = (S.nr == S.no) ? S.nr : 0;
-        if (shape == 4) cnt = poly_chunk<4, 4, STREAMED>(S, R, s_queue[warp], p, pair, c_begin, c_len, lane);
-        else if (shape == 3) cnt = poly_chunk<3, 3, STREAMED>(S, R, s_queue[warp], p, pair, c_begin, c_len, lane);
-        else if (shape == 6) cnt = poly_chunk<6, 6, STREAMED>(S, R, s_queue[warp], p, pair, c_begin, c_len, lane);
-        else if (shape == 8) cnt = poly_chunk<8, 8, STREAMED>(S, R, s_queue[warp], p, pair, c_begin, c_len, lane);
-        else cnt = poly_chunk<0, 0, STREAMED>(S, R, s_queue[warp], p, pair, c_begin, c_len, lane);
+        unsigned cnt;                                                  // first level with the robot's normals in registers
+        if (S.nr == 4) cnt = poly_chunk<4, STREAMED>(S, s_queue[warp], p, pair, c_begin, c_len, lane);
+        else if (S.nr == 3) cnt = poly_chunk<3, STREAMED>(S, s_queue[warp], p, pair, c_begin, c_len, lane);
+        else if (S.nr == 6) cnt = poly_chunk<6, STREAMED>(S, s_queue[warp], p, pair, c_begin, c_len, lane);
+        else if (S.nr == 8) cnt = poly_chunk<8, STREAMED>(S, s_queue[warp], p, pair, c_begin, c_len, lane);
+        else cnt = poly_chunk<0, STREAMED>(S, s_queue[warp], p, pair, c_begin, c_len, lane);
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (p.block_uniform) {
             if (lane == 0) s_part[warp] = cnt;
