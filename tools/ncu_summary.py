@@ -14,7 +14,9 @@ KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second", "launch__
         "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio"]
-for rep in sys.argv[1:]:
+args = [a for a in sys.argv[1:] if not a.startswith("--json=")]
+json_out = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--json=")), None)
+for rep in args:
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -26,3 +28,15 @@ for rep in sys.argv[1:]:
             if k in hdr:
                 i = hdr.index(k)
                 print(f"  {k:95s} {r[i]:>18s} {units[i]}")
+        if json_out:                                     # the figures bench.py quotes (first kernel of the first report)
+            import json
+            g = lambda k: float(r[hdr.index(k)].replace(",", "")) if k in hdr else None
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd, wr = g("dram__bytes_read.sum"), g("dram__bytes_write.sum")
+            rd = rd * scale.get(units[hdr.index("dram__bytes_read.sum")], 1.0) if rd is not None else None
+            wr = wr * scale.get(units[hdr.index("dram__bytes_write.sum")], 1.0) if wr is not None else None
+            json.dump({"report": rep, "kernel": name, "dram_bytes_read": rd, "dram_bytes_write": wr,
+                       "issue_active_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                       "inst_executed": g("smsp__inst_executed.sum"), "duration": g("gpu__time_duration.sum"),
+                       "duration_unit": units[hdr.index("gpu__time_duration.sum")]}, open(json_out, "w"), indent=1)
+            json_out = None

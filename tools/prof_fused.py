@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Short driver for ncu: a few launches of one counting kernel.  usage: prof_fused.py [fused|fused5|streamed3|streamed5|ztest|sweep|poly]"""
+"""Short driver for ncu: a few launches of one counting kernel.
+usage: prof_fused.py [fused|fused5|streamed3|streamed5|ztest|sweep|poly|cfg4|cfg2|adaptive]"""
 import importlib, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -23,6 +24,23 @@ elif mode == "poly":
     d_hits = torch.zeros(pp.size, dtype=torch.int64, device="cuda")
     for _ in range(3):
         ctx.count_fused_polygons(d_pairs, pp.size, 10_000, 7, d_hits)
+elif mode == "cfg4":                                   # one pair, long items: k_count<DirectSrc, false, DEFER, MULTI>
+    one = put(wl.cfg2_pair()); d_hits = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for _ in range(3):
+        ctx.count_fused(one, 1, 2_000_000_000, 7, d_hits)
+elif mode == "cfg2":                                   # one pair x 1e6: k_count<DirectSrc, false, false, MULTI> (packed arrival counters)
+    one = put(wl.cfg2_pair()); d_hits = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for _ in range(6):
+        ctx.count_fused(one, 1, 1_000_000, 7, d_hits)
+elif mode == "adaptive":                               # the whole adaptive loop: k_count<IndirectSrc,...> + k_ztest_compact per iteration
+    pairs = wl.dataset_pairs(100_000, 3)
+    rb, poses, sds, pi, si, pos = wl.reference_tables(pairs)
+    bins = np.array([0, 0.01, 0.1, 1.0], np.float32); acc = np.array([1e-4, 1e-3, 1e-2], np.float32)
+    dd = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (rb, poses.ravel(), sds.ravel(), pi, si, pos.ravel(), bins, acc)]
+    d_hits = torch.zeros(pairs.size, device="cuda")
+    it, drawn = ctx.adaptive_run(dd[0], dd[1], pairs.size, dd[2], pairs.size, dd[3], dd[4], dd[5], pairs.size, dd[6], dd[7], 4,
+                                 1_020_000, 1000, 20000, 100000, 7, d_hits)
+    print("iterations", it, "samples", drawn)
 elif mode in ("fused", "fused5", "ztest"):
     pairs = wl.dataset_pairs(100_000, 3, shape_variance=(mode == "fused5"))
     n = 1000 if mode == "ztest" else 10_000
@@ -37,4 +55,4 @@ else:
     for _ in range(4):
         ctx.count_streamed(d_pairs, npairs, z, npairs * n, ndof, n, d_hits, z_pair_stride=n)
 torch.cuda.synchronize()
-print(mode, "hits", int(d_hits.sum().item()), "launches", ctx.launch_count)
+print(mode, "sum", float(d_hits.sum().item()), "launches", ctx.launch_count)
