@@ -26,14 +26,19 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 50 --csv --log-file
     python tools/prof_fused.py cfg2 > /dev/null 2>&1
 
 # 4. full captures of the counting kernels (one launch each, after the same command ran clean above)
+# (the reports are condensed to text on the box: gpurun merges at most 64 MiB back; only the fused one travels whole)
 for m in fused fused5 cfg4 cfg2 sweep poly streamed3 streamed5; do
-    ncu --set full --clock-control none --import-source on -k regex:k_count --launch-skip 1 --launch-count 1 -f -o $O/${T}_ncu_$m \
+    ncu --set full --clock-control none --import-source on -k regex:k_count --launch-skip 1 --launch-count 1 -f -o /tmp/${T}_ncu_$m \
         python tools/prof_fused.py $m > /dev/null 2>&1
+    python tools/ncu_summary.py --json=$O/${T}_ncu_$m.json /tmp/${T}_ncu_$m.ncu-rep > $O/${T}_ncu_$m.txt 2>&1
 done
-ncu --set full --clock-control none --import-source on -k regex:IndirectSrc --launch-skip 22 --launch-count 1 -f -o $O/${T}_ncu_indirect \
+cp /tmp/${T}_ncu_fused.ncu-rep $O/
+ncu --set full --clock-control none --import-source on -k regex:IndirectSrc --launch-skip 4 --launch-count 1 -f -o /tmp/${T}_ncu_indirect \
     python tools/prof_fused.py adaptive > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_ztest_compact --launch-skip 2 --launch-count 1 -f -o $O/${T}_ncu_ztest_compact \
+python tools/ncu_summary.py /tmp/${T}_ncu_indirect.ncu-rep > $O/${T}_ncu_indirect.txt 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_ztest_compact --launch-skip 2 --launch-count 1 -f -o /tmp/${T}_ncu_ztest_compact \
     python tools/prof_fused.py adaptive > /dev/null 2>&1
+python tools/ncu_summary.py /tmp/${T}_ncu_ztest_compact.ncu-rep > $O/${T}_ncu_ztest_compact.txt 2>&1
 
 # 5. the drop-in programs: where the time goes
 rm -rf /tmp/gd && ( time $P/host/generate_dataset --data_dir /tmp/gd -n 100 --seed 1 --stats ) 2>&1 | tr '\r' '\n' | grep -E 'stats|real' > $O/${T}_programs.txt
