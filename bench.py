@@ -614,6 +614,7 @@ def programs_gpu_count_invariance(dist, rank, world):
                            "process start-up and CUDA/NCCL initialisation"}
             if not same:
                 raise RuntimeError("ztest output depends on the number of GPUs")
+            res["single_process_group"] = single_process_group(world)
         except Exception as e:                                # reported, not fatal for the bench line
             res = {"error": str(e)[:400]}
         finally:
@@ -622,6 +623,36 @@ def programs_gpu_count_invariance(dist, rank, world):
     else:
         store.wait(["satmc_programs_done"])
     return res
+
+
+def single_process_group(world):
+    """ONE process driving all N GPUs (satmc_group_create), cfg 4 through host buffers: sample ranges combined either by the
+    counting kernels' own epilogue (system-scope atomics into device 0's memory over NVLink, no collective launch) or by
+    ncclAllReduce.  Wall clock per call, host buffers in and out; a 1e7-sample call exposes the fixed cost of each path."""
+    mod = importlib.import_module(PKG)
+    wl = importlib.import_module(PKG + ".workloads")
+    one = wl.cfg2_pair()
+    out = {}
+    with mod.Group(devices=list(range(world))) as g:
+        ref = None
+        for label, on in (("peer_atomics", True), ("nccl", False)):
+            g.set_peer_reduce(on)
+            g.count_fused_host(one, 2_000_000_000, 3, mod.SHARD_BY_SAMPLE_RANGE)
+            t0 = time.perf_counter()
+            for s_ in range(2):
+                big = g.count_fused_host(one, 100_000_000_000, 1000 + s_, mod.SHARD_BY_SAMPLE_RANGE)
+            t_big = (time.perf_counter() - t0) / 2
+            ts = []
+            for s_ in range(60):
+                t0 = time.perf_counter()
+                small = g.count_fused_host(one, 10_000_000, 7, mod.SHARD_BY_SAMPLE_RANGE)
+                ts.append(time.perf_counter() - t0)
+            out[label] = {"exchange": g.last_exchange(), "cfg4_1e11_ms_per_call": t_big * 1e3, "cfg4_1e11_tests_per_s": 1e11 / t_big,
+                          "call_1e7_samples_us": float(np.median(ts[10:])) * 1e6, "count_1e11": int(big[0]), "count_1e7": int(small[0])}
+            ref = ref or (int(big[0]), int(small[0]))
+            out[label]["same_counts_as_first_path"] = bool((int(big[0]), int(small[0])) == ref)
+    out["what"] = "satmc_group_count_fused_host on N GPUs from one process: wall clock incl. H2D of the pair and D2H of the count"
+    return out
 
 
 def extras(ctx, mod, wl, torch, hbm_peak, src):

@@ -57,7 +57,7 @@ ABI_SYMBOLS = (
     "satmc_group_synchronize", "satmc_group_world", "satmc_group_local_count", "satmc_group_rank", "satmc_group_context",
     "satmc_group_last_error", "satmc_group_nccl_version", "satmc_group_hits_capacity", "satmc_group_count_fused",
     "satmc_group_count_fused_host", "satmc_group_set_timing", "satmc_group_last_times", "satmc_group_set_tables",
-    "satmc_group_adaptive_run_host",
+    "satmc_group_adaptive_run_host", "satmc_group_last_exchange", "satmc_group_set_peer_reduce",
 )
 
 
@@ -134,6 +134,8 @@ def load_library() -> ctypes.CDLL:
         "satmc_group_count_fused": (i32, [vp, c.POINTER(vp), u64, u64, u64, u64, u32, i32, c.POINTER(vp), u32]),
         "satmc_group_count_fused_host": (i32, [vp, vp, u64, u64, u64, u64, u32, i32, vp, u32]),
         "satmc_group_set_timing": (i32, [vp, i32]),
+        "satmc_group_last_exchange": (i32, [vp]),
+        "satmc_group_set_peer_reduce": (i32, [vp, i32]),
         "satmc_group_last_times": (i32, [vp, c.POINTER(c.c_float), c.POINTER(c.c_float)]),
         "satmc_group_set_tables": (i32, [vp, f32p, f32p, u32, f32p, u32, f32p, f32p, i32]),
         "satmc_group_adaptive_run_host": (i32, [vp, f32p, f32p, f32p, i32, i32, i32, i32, i32, u64, u32, f32p, c.POINTER(i32),
@@ -440,6 +442,13 @@ class Group:
 
     def hits_capacity(self, n_pairs: int) -> int:
         return int(self._lib.satmc_group_hits_capacity(self._h, n_pairs))
+
+    def set_peer_reduce(self, on: bool) -> None:
+        """Allow / forbid the collective-free sample-range reduction over peer memory (count_fused_host, one process)."""
+        self._check(self._lib.satmc_group_set_peer_reduce(self._h, int(bool(on))))
+
+    def last_exchange(self) -> str:
+        return {0: "none", 1: "nccl", 2: "peer_atomics"}[int(self._lib.satmc_group_last_exchange(self._h))]
 
     def set_timing(self, on: bool) -> None:
         self._check(self._lib.satmc_group_set_timing(self._h, int(bool(on))))

@@ -387,8 +387,11 @@ static int check_streamed_args(satmc_ctx* ctx, const void* pairs, const void* z,
 
 extern "C" {
 
-int satmc_count_fused(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pairs, uint64_t n_samples, uint64_t seed,
-                      uint64_t sample_offset, uint32_t pair_id_offset, uint64_t* d_hits, uint32_t flags)
+}  // extern "C"
+
+// satmc_count_fused with the internal flags allowed (SATMC_PEER_ATOMIC_OUT, used by the group code)
+int satmc_count_fused_impl(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pairs, uint64_t n_samples, uint64_t seed,
+                           uint64_t sample_offset, uint32_t pair_id_offset, uint64_t* d_hits, uint32_t flags)
 {
     if (!ctx) return fail(nullptr, SATMC_ERR_INVALID, "ctx is NULL");
     if ((!d_pairs || !d_hits) && n_pairs) return fail(ctx, SATMC_ERR_INVALID, "null pointer argument");
@@ -400,6 +403,25 @@ int satmc_count_fused(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pair
     philox_expand_key((uint32_t)seed, (uint32_t)(seed >> 32), p.keys); p.flags = flags;
     p.hits = reinterpret_cast<unsigned long long*>(d_hits); p.exact_evals = ctx->d_exact_evals;
     return launch_count<DirectSrc, false>(ctx, DirectSrc{d_pairs}, p, ctx->profiling);
+}
+
+// would a fused call of this shape be cut into several work items per pair (the kernels with the accumulate / finalize
+// epilogue, which is where SATMC_PEER_ATOMIC_OUT is honoured)?
+bool satmc_fused_is_multi(satmc_ctx* ctx, uint64_t n_pairs, uint64_t n_samples)
+{
+    CountParams p{}; p.n_pairs = n_pairs; p.n_samples = n_samples;
+    uint64_t blocks = 0;
+    if (n_pairs == 0 || n_samples == 0 || plan_items(ctx, p, ctx->blocks_per_sm, blocks, 8, 1ull << 20)) return false;
+    return p.n_chunks > 1;
+}
+
+extern "C" {
+
+int satmc_count_fused(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pairs, uint64_t n_samples, uint64_t seed,
+                      uint64_t sample_offset, uint32_t pair_id_offset, uint64_t* d_hits, uint32_t flags)
+{
+    return satmc_count_fused_impl(ctx, d_pairs, n_pairs, n_samples, seed, sample_offset, pair_id_offset, d_hits,
+                                  flags & (SATMC_ACCUMULATE | SATMC_EXACT_ONLY));
 }
 
 int satmc_count_streamed(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pairs, const float* d_z, uint64_t ldz,

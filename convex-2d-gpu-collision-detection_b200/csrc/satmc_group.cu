@@ -99,6 +99,9 @@ struct satmc_group {
     uint32_t n_poses = 0, n_std = 0; int n_bins = 0;
     float kernel_ms = -1.f, collective_ms = -1.f;
     bool timing = false;
+    int p2p = 0;                                 // 0 not probed, 1 every local device can reach device 0's memory, -1 no
+    bool use_p2p = true;
+    int last_exchange = SATMC_EXCHANGE_NONE;
 };
 
 namespace {
@@ -230,6 +233,25 @@ int all_gather(satmc_group* g, std::vector<void*>& bufs, size_t chunk, size_t el
     return SATMC_OK;
 }
 
+// Peer access from every local device to local device 0 (NVLink / NVSwitch): probed and enabled once.
+bool p2p_ready(satmc_group* g)
+{
+    if (g->p2p != 0) return g->p2p > 0;
+    g->p2p = -1;
+    const int root = g->dev[0].ctx->device;
+    for (size_t l = 1; l < g->dev.size(); l++) {
+        int can = 0;
+        const int d = g->dev[l].ctx->device;
+        if (cudaDeviceCanAccessPeer(&can, d, root) != cudaSuccess || !can) { cudaGetLastError(); return false; }
+        if (cudaSetDevice(d) != cudaSuccess) { cudaGetLastError(); return false; }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(root, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return false; }
+        cudaGetLastError();
+    }
+    g->p2p = 1;
+    return true;
+}
+
 int sync_all(satmc_group* g)
 {
     for (Local& L : g->dev) { GCU(g, cudaSetDevice(L.ctx->device)); GCU(g, cudaStreamSynchronize(L.stream)); }
@@ -340,6 +362,15 @@ int satmc_group_nccl_version(void)
     return v;
 }
 
+int satmc_group_set_peer_reduce(satmc_group* g, int enabled)
+{
+    if (!g) return gfail(nullptr, SATMC_ERR_INVALID, "group is NULL");
+    g->use_p2p = enabled != 0;
+    return SATMC_OK;
+}
+
+int satmc_group_last_exchange(const satmc_group* g) { return g ? g->last_exchange : SATMC_EXCHANGE_NONE; }
+
 int satmc_group_set_timing(satmc_group* g, int enabled)
 {
     if (!g) return gfail(nullptr, SATMC_ERR_INVALID, "group is NULL");
@@ -446,8 +477,40 @@ int satmc_group_count_fused_host(satmc_group* g, const satmc_pair* h_pairs, uint
     }
     // a single process reads every slice from the device that computed it; no collective is needed by pair
     const bool direct = (shard_mode == SATMC_SHARD_BY_PAIR) && (int)nl == g->world;
+    // Sample ranges inside one process, few pairs (every shard is cut into several work items per pair): the compute
+    // kernels themselves finish into ONE counter array in device 0's memory with system-scope atomics over NVLink --
+    // the reduction is the kernels' own epilogue, no collective is launched.
+    bool peer = (shard_mode == SATMC_SHARD_BY_SAMPLE_RANGE) && (int)nl == g->world && g->world > 1 && g->use_p2p && !(flags & SATMC_ACCUMULATE);
+    if (peer) {
+        for (size_t l = 0; l < nl && peer; l++) {
+            uint64_t lo = 0, hi = 0;
+            satmc_shard_range(shard_mode, n_samples, g->world, g->rank0 + (int)l, &lo, &hi);
+            peer = hi == lo || satmc_fused_is_multi(g->dev[l].ctx, n_pairs, hi - lo);
+        }
+        peer = peer && p2p_ready(g);
+    }
     int rc = SATMC_OK;
-    if (direct) {
+    g->last_exchange = g->world == 1 || direct ? SATMC_EXCHANGE_NONE : (peer ? SATMC_EXCHANGE_PEER_ATOMICS : SATMC_EXCHANGE_NCCL);
+    if (peer) {
+        Local& R = g->dev[0];
+        GCU(g, cudaSetDevice(R.ctx->device));
+        GCU(g, cudaMemsetAsync(dh[0], 0, n_pairs * sizeof(uint64_t), R.stream));
+        GCU(g, cudaEventRecord(R.ev[0], R.stream));
+        for (size_t l = 0; l < nl; l++) {
+            Local& L = g->dev[l];
+            GCU(g, cudaSetDevice(L.ctx->device));
+            if (l > 0) GCU(g, cudaStreamWaitEvent(L.stream, R.ev[0], 0));
+            uint64_t lo = 0, hi = 0;
+            satmc_shard_range(shard_mode, n_samples, g->world, g->rank0 + (int)l, &lo, &hi);
+            if (hi > lo)
+                GSAT(g, l, satmc_count_fused_impl(L.ctx, dp[l], n_pairs, hi - lo, seed, sample_offset + lo, pair_id_offset, dh[0],
+                                                  (flags & SATMC_EXACT_ONLY) | SATMC_PEER_ATOMIC_OUT));
+            if (l > 0) GCU(g, cudaEventRecord(L.ev[1], L.stream));
+        }
+        GCU(g, cudaSetDevice(R.ctx->device));
+        for (size_t l = 1; l < nl; l++) GCU(g, cudaStreamWaitEvent(R.stream, g->dev[l].ev[1], 0));
+        GCU(g, cudaMemcpyAsync(h_hits, dh[0], n_pairs * sizeof(uint64_t), cudaMemcpyDeviceToHost, R.stream));
+    } else if (direct) {
         for (size_t l = 0; l < nl && rc == SATMC_OK; l++) {
             Local& L = g->dev[l];
             GCU(g, cudaSetDevice(L.ctx->device));

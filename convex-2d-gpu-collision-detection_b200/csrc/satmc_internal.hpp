@@ -87,3 +87,9 @@ struct DeviceGuard {
     explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
+
+// internal entry points shared with the group code (satmc_group.cu)
+#define SATMC_PEER_ATOMIC_OUT 0x80000000u
+int satmc_count_fused_impl(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t n_pairs, uint64_t n_samples, uint64_t seed,
+                           uint64_t sample_offset, uint32_t pair_id_offset, uint64_t* d_hits, uint32_t flags);
+bool satmc_fused_is_multi(satmc_ctx* ctx, uint64_t n_pairs, uint64_t n_samples);

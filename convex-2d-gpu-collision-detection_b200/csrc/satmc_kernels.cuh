@@ -137,6 +137,10 @@ __device__ __forceinline__ unsigned long long* counter_base(const CountParams& p
 // barrier at the end of the kernel (a cfg 2 call is ~15 us in all, of which the fence + arrival + exchange chain of
 // finalize_counters was ~3).  The host guarantees arrivals < 2^24 and hits per counter < 2^40.
 constexpr int kPackShift = 40;
+// internal flag (never accepted from callers): the totals are ADDED to p.hits with system-scope atomics, because p.hits
+// is one array in the memory of a peer GPU that several devices finish into (satmc_group_count_fused_host, sample-range
+// sharding inside one process: the compute kernel's own epilogue is the reduction over NVLink, no collective launch).
+#define SATMC_PEER_ATOMIC_OUT 0x80000000u
 __device__ __forceinline__ void packed_arrive(const CountParams& p, uint64_t counter, unsigned long long c)
 {
     const unsigned long long add = (1ull << kPackShift) | c;
@@ -144,7 +148,9 @@ __device__ __forceinline__ void packed_arrive(const CountParams& p, uint64_t cou
     if ((unsigned)(old >> kPackShift) + 1u == p.arrivals) {
         const unsigned long long total = (old + add) & ((1ull << kPackShift) - 1ull);
         SATMC_ASSERT(counter < p.hits_len);
-        if (p.flags & SATMC_ACCUMULATE) p.hits[counter] += total; else p.hits[counter] = total;
+        if (p.flags & SATMC_PEER_ATOMIC_OUT) atomicAdd_system(p.hits + counter, total);
+        else if (p.flags & SATMC_ACCUMULATE) p.hits[counter] += total;
+        else p.hits[counter] = total;
         p.acc[counter] = 0ull;
     }
 }
@@ -167,7 +173,9 @@ __device__ __noinline__ void finalize_counters_slow(const CountParams& p)
         const uint64_t off = (i / p.fin_inner) * p.fin_stride + i % p.fin_inner;
         const unsigned long long v = atomicExch(p.acc + off, 0ull);
         SATMC_ASSERT(off < p.hits_len);
-        if (p.flags & SATMC_ACCUMULATE) p.hits[off] += v; else p.hits[off] = v;
+        if (p.flags & SATMC_PEER_ATOMIC_OUT) atomicAdd_system(p.hits + off, v);
+        else if (p.flags & SATMC_ACCUMULATE) p.hits[off] += v;
+        else p.hits[off] = v;
     }
     if (threadIdx.x == 0) *p.blocks_done = 0u;
 }

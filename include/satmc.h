@@ -299,6 +299,17 @@ int satmc_group_count_fused(satmc_group* g, const satmc_pair* const* d_pairs, ui
 int satmc_group_count_fused_host(satmc_group* g, const satmc_pair* h_pairs, uint64_t n_pairs, uint64_t n_samples,
                                  uint64_t seed, uint64_t sample_offset, uint32_t pair_id_offset, int shard_mode,
                                  uint64_t* h_hits, uint32_t flags);
+/* How the last satmc_group_count_fused_host call combined the shards: nothing to combine (one device, or disjoint
+ * slices read back directly), an NCCL collective, or -- sample ranges inside one process with few pairs -- no collective
+ * at all: every device's counting kernel finishes into one counter array in device 0's memory with system-scope
+ * atomics over NVLink (the reduction is the compute kernel's own epilogue).  satmc_group_set_peer_reduce(g, 0) forces
+ * the NCCL path (for comparison); the counts are identical either way. */
+#define SATMC_EXCHANGE_NONE          0
+#define SATMC_EXCHANGE_NCCL          1
+#define SATMC_EXCHANGE_PEER_ATOMICS  2
+int satmc_group_last_exchange(const satmc_group* g);
+int satmc_group_set_peer_reduce(satmc_group* g, int enabled);
+
 /* With timing enabled satmc_group_count_fused brackets local device 0's kernel and the collective with CUDA events
  * (and waits for them): the split of a step into compute and exchange that bench.py reports (allreduce_us). */
 int satmc_group_set_timing(satmc_group* g, int enabled);

@@ -41,6 +41,17 @@ def test_group_counts_equal_single_gpu(ctx, dev, satmc, workloads, torch_cuda, w
         for mode in (satmc.SHARD_BY_PAIR, satmc.SHARD_BY_SAMPLE_RANGE):
             got = g.count_fused_host(pairs, n, seed, mode, sample_offset=off, pair_id_offset=pid)
             np.testing.assert_array_equal(got, want, err_msg=f"host, mode {mode}")
+        # sample ranges, few pairs, one process: the kernels finish into device 0's memory over NVLink (no collective);
+        # with that path switched off the same call goes through ncclAllReduce -- same counts
+        if world > 1:
+            assert g.last_exchange() == "peer_atomics"
+            g.set_peer_reduce(False)
+            got = g.count_fused_host(pairs, n, seed, satmc.SHARD_BY_SAMPLE_RANGE, sample_offset=off, pair_id_offset=pid)
+            assert g.last_exchange() == "nccl"
+            np.testing.assert_array_equal(got, want, err_msg="host, sample ranges through NCCL")
+            g.set_peer_reduce(True)
+        else:
+            assert g.last_exchange() == "none"
         # resident inputs: the full pair array on every device, capacity-sized counters
         cap = g.hits_capacity(pairs.size)
         dp, dh = [], []
@@ -69,7 +80,11 @@ def test_group_single_pair_cfg4_slice(ctx, dev, satmc, workloads, torch_cuda):
     want = fused(ctx, dev, one, 2_000_000_000, 4)
     with satmc.Group(devices=list(range(world))) as g:
         got = g.count_fused_host(one, 2_000_000_000, 4, satmc.SHARD_BY_SAMPLE_RANGE)
+        assert g.last_exchange() == ("peer_atomics" if world > 1 else "none")
+        g.set_peer_reduce(False)
+        got2 = g.count_fused_host(one, 2_000_000_000, 4, satmc.SHARD_BY_SAMPLE_RANGE)
     np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(got2, want)
     assert abs(int(want[0]) / 2e9 - 0.166) < 0.01
 
 
