@@ -33,7 +33,7 @@ for m in fused fused5 cfg4 cfg2 sweep poly streamed3 streamed5; do
     python tools/ncu_summary.py --json=$O/${T}_ncu_$m.json /tmp/${T}_ncu_$m.ncu-rep > $O/${T}_ncu_$m.txt 2>&1
 done
 cp /tmp/${T}_ncu_fused.ncu-rep $O/
-ncu --set full --clock-control none --import-source on -k regex:IndirectSrc --launch-skip 4 --launch-count 1 -f -o /tmp/${T}_ncu_indirect \
+ncu --set full --clock-control none --import-source on -k regex:k_count --launch-skip 8 --launch-count 1 -f -o /tmp/${T}_ncu_indirect \
     python tools/prof_fused.py adaptive > /dev/null 2>&1
 python tools/ncu_summary.py /tmp/${T}_ncu_indirect.ncu-rep > $O/${T}_ncu_indirect.txt 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_ztest_compact --launch-skip 2 --launch-count 1 -f -o /tmp/${T}_ncu_ztest_compact \
