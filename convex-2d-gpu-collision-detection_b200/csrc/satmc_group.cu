@@ -102,6 +102,7 @@ struct satmc_group {
     int p2p = 0;                                 // 0 not probed, 1 every local device can reach device 0's memory, -1 no
     bool use_p2p = true;
     int last_exchange = SATMC_EXCHANGE_NONE;
+    bool peer_acc_dirty = false;                 // a call failed between the kernels and the re-clearing of the accumulator
 };
 
 namespace {
@@ -492,24 +493,33 @@ int satmc_group_count_fused_host(satmc_group* g, const satmc_pair* h_pairs, uint
     int rc = SATMC_OK;
     g->last_exchange = g->world == 1 || direct ? SATMC_EXCHANGE_NONE : (peer ? SATMC_EXCHANGE_PEER_ATOMICS : SATMC_EXCHANGE_NCCL);
     if (peer) {
+        // The accumulator in device 0's memory holds zeros between calls (cleared when allocated and again right after
+        // every read-out, which the end-of-call synchronisation covers), so every device's kernel starts at once: no
+        // memset and no event in front of them.  Device 0 only waits for the others' kernels before it reads the totals.
         Local& R = g->dev[0];
         GCU(g, cudaSetDevice(R.ctx->device));
-        GCU(g, cudaMemsetAsync(dh[0], 0, n_pairs * sizeof(uint64_t), R.stream));
-        GCU(g, cudaEventRecord(R.ev[0], R.stream));
+        const size_t had = R.cap[3];
+        void* accv = nullptr;
+        rc = dev_buf(g, R, 3, n_pairs * sizeof(uint64_t), &accv);
+        if (rc) return rc;
+        if (R.cap[3] != had || g->peer_acc_dirty) { GCU(g, cudaMemsetAsync(accv, 0, R.cap[3], R.stream)); GCU(g, cudaStreamSynchronize(R.stream)); }
+        g->peer_acc_dirty = true;
+        uint64_t* acc = static_cast<uint64_t*>(accv);
         for (size_t l = 0; l < nl; l++) {
             Local& L = g->dev[l];
             GCU(g, cudaSetDevice(L.ctx->device));
-            if (l > 0) GCU(g, cudaStreamWaitEvent(L.stream, R.ev[0], 0));
             uint64_t lo = 0, hi = 0;
             satmc_shard_range(shard_mode, n_samples, g->world, g->rank0 + (int)l, &lo, &hi);
             if (hi > lo)
-                GSAT(g, l, satmc_count_fused_impl(L.ctx, dp[l], n_pairs, hi - lo, seed, sample_offset + lo, pair_id_offset, dh[0],
+                GSAT(g, l, satmc_count_fused_impl(L.ctx, dp[l], n_pairs, hi - lo, seed, sample_offset + lo, pair_id_offset, acc,
                                                   (flags & SATMC_EXACT_ONLY) | SATMC_PEER_ATOMIC_OUT));
             if (l > 0) GCU(g, cudaEventRecord(L.ev[1], L.stream));
         }
         GCU(g, cudaSetDevice(R.ctx->device));
         for (size_t l = 1; l < nl; l++) GCU(g, cudaStreamWaitEvent(R.stream, g->dev[l].ev[1], 0));
-        GCU(g, cudaMemcpyAsync(h_hits, dh[0], n_pairs * sizeof(uint64_t), cudaMemcpyDeviceToHost, R.stream));
+        GCU(g, cudaMemcpyAsync(h_hits, acc, n_pairs * sizeof(uint64_t), cudaMemcpyDeviceToHost, R.stream));
+        GCU(g, cudaMemsetAsync(acc, 0, n_pairs * sizeof(uint64_t), R.stream));
+        g->peer_acc_dirty = false;
     } else if (direct) {
         for (size_t l = 0; l < nl && rc == SATMC_OK; l++) {
             Local& L = g->dev[l];
