@@ -56,7 +56,7 @@ def sass_constants():
     """Instruction mix of the fused 3-DoF hot loop (one trip = one 4-sample group per lane), from the committed artefact
     that tools/sass_count.py writes; the loop with 50..60 IMAD.WIDE is the 3-DoF one (3 Philox calls)."""
     path = os.path.join(ROOT, "profiles", "r2_sass_k_count_hotloop.json")
-    out = {"instr_per_group": 335.0, "imad_wide_per_group": 53.0, "mufu_per_group": 32.0, "fp32_per_group": 136.0,
+    out = {"instr_per_group": 302.0, "imad_wide_per_group": 53.0, "mufu_per_group": 32.0, "fp32_per_group": 67.0, "fp32x2_per_group": 34.0,
            "source": "built-in defaults (profiles/r2_sass_k_count_hotloop.json missing)"}
     try:
         with open(path) as f:
@@ -68,6 +68,7 @@ def sass_constants():
                 if 45 <= L["imad_wide"] <= 60:
                     out = {"instr_per_group": float(L["instr"]), "imad_wide_per_group": float(L["imad_wide"]),
                            "mufu_per_group": float(L["mufu"]), "fp32_per_group": float(L["fp32"]),
+                           "fp32x2_per_group": float(L.get("fp32x2", 0)),
                            "source": "profiles/r2_sass_k_count_hotloop.json (tools/sass_count.py on the shipped libsatmc.so)"}
     except (OSError, KeyError, ValueError):
         pass
@@ -432,10 +433,13 @@ def main():
                 "frac_issue_weighted": per_gpu * weighted_per_test / lane_peak,
                 "frac_issue_weighted_note": "IMAD.WIDE counted as 4 slots (it blocks issue for ~4 clk): how close the loop is to the bound "
                                             "its own instruction mix allows; ~1 means no headroom without fewer wide multiplies",
-                "frac_fma_pipe": per_gpu * (sc["fp32_per_group"] + 4.0 * sc["imad_wide_per_group"]) / 4.0 / lane_peak,
+                "frac_fma_pipe": per_gpu * (sc["fp32_per_group"] + 2.0 * sc["fp32x2_per_group"] + 4.0 * sc["imad_wide_per_group"]) / 4.0 / lane_peak,
+                "frac_fma_pipe_note": "FMA-pipe cycles: scalar FP32 1, packed FP32 (FFMA2/FMUL2, two operations per issue slot) 2, IMAD.WIDE 4",
                 "frac_vs_survey_w8_model": per_gpu * SURVEY_I_FMA_W8 / lane_peak,
                 "frac_vs_survey_w4_model": per_gpu * SURVEY_I_FMA_W4 / lane_peak,
-                "note": "frac is plain issue-slot utilisation (warp-instructions issued / issue slots available); the last two are "
+                "note": "frac is plain issue-slot utilisation (warp-instructions issued / issue slots available). Since round 2 the "
+                        "screening arithmetic is packed FP32: fewer issued instructions for the same work, so the kernel got faster "
+                        "(3.34 -> 3.23 ms) while this utilisation figure FELL (0.68 -> 0.63); the last two are "
                         "against SURVEY.md 8(d)'s models (247 / 163 FMA-pipe instructions per test) and exceed 1 because a 22-FP-op "
                         "conservative screening test decides 99.98 % of the samples and only the rest run the exact 8-axis SAT",
             },

@@ -59,6 +59,14 @@ __device__ __forceinline__ float min3_nan_abs(float a, float b, float c)
     return d;
 }
 
+// max(|a|, |b|, |c|) that returns NaN if any input is NaN (FMNMX3.NAN)
+__device__ __forceinline__ float max3_nan_abs(float a, float b, float c)
+{
+    float d;
+    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)));
+    return d;
+}
+
 // ---------------------------------------------------------------------------------------------
 // exact reference arithmetic
 // ---------------------------------------------------------------------------------------------
@@ -264,6 +272,47 @@ __device__ __forceinline__ float screen_gap(const PairConst& P, float z0, float 
     float s, c;
     screen_trig(P.nst, P.th, z2, s, c);
     return screen_gap_sc<NDOF>(P, z0, z1, s, c, z3, z4, hmin);
+}
+
+// Two samples at once in packed FP32: the same operations with the same roundings as two screen_gap<NDOF> calls
+// (fma.rn.f32x2 is IEEE round-to-nearest per lane), a quarter fewer instructions -- and the packed ones overlap with the
+// ALU-pipe instructions around them (fused cfg 3: 3.34 -> 3.23 ms).  The four gaps |u| - e stay scalar (operand |.| has
+// no packed form).  z3 / z4 are read only for NDOF = 5.
+template <int NDOF>
+__device__ __forceinline__ void screen_gap_pair(const PairConst& P, float z0a, float z1a, float z2a, float z3a, float z4a,
+                                                float z0b, float z1b, float z2b, float z3b, float z4b,
+                                                float& m_a, float& m_b, float& hmin_a, float& hmin_b)
+{
+    const f32x2 phi = fma2(dup2(P.nst), pack2(z2a, z2b), dup2(P.th));
+    const float sa = __sinf(lo2(phi)), ca = __cosf(lo2(phi)), sb = __sinf(hi2(phi)), cb = __cosf(hi2(phi));
+    const f32x2 c2 = pack2(ca, cb), s2 = pack2(sa, sb), ns2 = pack2(-sa, -sb);
+    const f32x2 z0 = pack2(z0a, z0b), z1 = pack2(z1a, z1b);
+    const f32x2 ua0 = fma2(dup2(P.nkx0), z0, fma2(dup2(P.nky0), z1, dup2(P.pa0)));
+    const f32x2 ua1 = fma2(dup2(P.kx1), z0, fma2(dup2(P.nky1), z1, dup2(P.pa1)));
+    const f32x2 ub0 = fma2(c2, ua0, mul2(ns2, ua1));
+    const f32x2 ub1 = fma2(s2, ua0, mul2(c2, ua1));
+    const f32x2 C = pack2(fabsf(ca), fabsf(cb)), S = pack2(fabsf(sa), fabsf(sb));
+    const f32x2 a0 = dup2(P.a0), a1 = dup2(P.a1);
+    f32x2 hx = dup2(P.b0), hy = dup2(P.b1);
+    hmin_a = hmin_b = fminf(P.b0, P.b1);
+    if (NDOF == 5) {                              // a perturbation past -width flips the corner order but spans the same rectangle
+        const f32x2 qx = fma2(pack2(z3a, z3b), dup2(P.hw), hx), qy = fma2(pack2(z4a, z4b), dup2(P.hh), hy);
+        hx = pack2(fabsf(lo2(qx)), fabsf(hi2(qx))); hy = pack2(fabsf(lo2(qy)), fabsf(hi2(qy)));
+        hmin_a = fminf(lo2(hx), lo2(hy)); hmin_b = fminf(hi2(hx), hi2(hy));
+    }
+    const f32x2 eb0 = fma2(a0, C, fma2(a1, S, hx));
+    const f32x2 eb1 = fma2(a0, S, fma2(a1, C, hy));
+    const f32x2 ea0 = fma2(hx, C, fma2(hy, S, a0));
+    const f32x2 ea1 = fma2(hx, S, fma2(hy, C, a1));
+    m_a = fmaxf(fmaxf(fabsf(lo2(ub0)) - lo2(eb0), fabsf(lo2(ub1)) - lo2(eb1)), fmaxf(fabsf(lo2(ua0)) - lo2(ea0), fabsf(lo2(ua1)) - lo2(ea1)));
+    m_b = fmaxf(fmaxf(fabsf(hi2(ub0)) - hi2(eb0), fabsf(hi2(ub1)) - hi2(eb1)), fmaxf(fabsf(hi2(ua0)) - hi2(ea0), fabsf(hi2(ua1)) - hi2(ea1)));
+}
+
+__device__ __forceinline__ void screen_gap_pair3(const PairConst& P, float z0a, float z1a, float z2a, float z0b, float z1b, float z2b,
+                                                 float& m_a, float& m_b)
+{
+    float ha, hb;
+    screen_gap_pair<3>(P, z0a, z1a, z2a, 0.f, 0.f, z0b, z1b, z2b, 0.f, 0.f, m_a, m_b, ha, hb);
 }
 
 // true iff the sign of m is provably the exact decision (false for NaN anywhere)

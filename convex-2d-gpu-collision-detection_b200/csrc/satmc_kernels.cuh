@@ -252,6 +252,14 @@ __device__ __noinline__ unsigned fused_group_cold(ColdQueue* Q, unsigned pair_sl
     return fused_group_slow<D>(Pcold, robot, g, 0xFu, pid, K, exact_evals);
 }
 
+// packed FP32 screening in the fused hot loop (3-DoF: cfg 3 3.34 -> 3.23 ms, single pair 293 -> 314 Gtests/s); the
+// packed Box-Muller arithmetic (SATMC_BM_PACKED, satmc_sampler.cuh) costs more register moves than it saves
+#ifndef SATMC_FUSED_PACKED
+#define SATMC_FUSED_PACKED 1
+#endif
+#ifndef SATMC_FUSED_PACKED5
+#define SATMC_FUSED_PACKED5 1
+#endif
 // hot path: all four samples of group g
 template <int D, bool DEFER>
 __device__ __forceinline__ unsigned fused_group(const PairConst& P, const PairConst& Pcold, const float* robot, uint64_t g,
@@ -262,13 +270,30 @@ __device__ __forceinline__ unsigned fused_group(const PairConst& P, const PairCo
     group_normals<D>((uint32_t)g, (uint32_t)(g >> 32), pid, K, n);
     unsigned cnt = 0;
     bool decided = true;
+    if constexpr (SATMC_FUSED_PACKED != 0 && D == 3) {              // samples in pairs, packed FP32 (screen_gap_pair)
+        float m0, m1, m2, m3;
+        screen_gap_pair3(P, n[0], n[1], n[2], n[3], n[4], n[5], m0, m1);
+        screen_gap_pair3(P, n[6], n[7], n[8], n[9], n[10], n[11], m2, m3);
+        cnt = (__float_as_uint(m0) >> 31) + (__float_as_uint(m1) >> 31) + (__float_as_uint(m2) >> 31) + (__float_as_uint(m3) >> 31);
+        decided = min3_nan_abs(min3_nan_abs(CUDART_INF_F, m0, m1), m2, m3) > P.eps;    // NaN-propagating: false for NaN
+    } else if constexpr (SATMC_FUSED_PACKED != 0 && SATMC_FUSED_PACKED5 != 0 && D == 5) {
+        float m[4], h[4];
+        screen_gap_pair<5>(P, n[0], n[1], n[2], n[3], n[4], n[5], n[6], n[7], n[8], n[9], m[0], m[1], h[0], h[1]);
+        screen_gap_pair<5>(P, n[10], n[11], n[12], n[13], n[14], n[15], n[16], n[17], n[18], n[19], m[2], m[3], h[2], h[3]);
 #pragma unroll
-    for (int t = 0; t < 4; t++) {
-        const float z3 = (D == 5) ? n[D * t + 3] : 0.0f, z4 = (D == 5) ? n[D * t + 4] : 0.0f;
-        float hmin;
-        const float m = screen_gap<D>(P, n[D * t], n[D * t + 1], n[D * t + 2], z3, z4, hmin);
-        cnt += __float_as_uint(m) >> 31;                            // m < 0 (m = -0 / NaN are undecided anyway)
-        decided = decided && screen_decided<D>(P, m, hmin);
+        for (int t = 0; t < 4; t++) {
+            cnt += __float_as_uint(m[t]) >> 31;
+            decided = decided && screen_decided<5>(P, m[t], h[t]);
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const float z3 = (D == 5) ? n[D * t + 3] : 0.0f, z4 = (D == 5) ? n[D * t + 4] : 0.0f;
+            float hmin;
+            const float m = screen_gap<D>(P, n[D * t], n[D * t + 1], n[D * t + 2], z3, z4, hmin);
+            cnt += __float_as_uint(m) >> 31;                        // m < 0 (m = -0 / NaN are undecided anyway)
+            decided = decided && screen_decided<D>(P, m, hmin);
+        }
     }
     if (!decided)                                                   // rare: redo the group, now or (DEFER) in cold_flush
         cnt = DEFER ? fused_group_cold<D>(Q, pair_slot, Pcold, robot, g, pid, K, exact_evals)
@@ -534,6 +559,9 @@ __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED
 // memory instead of registers (32 warps x 2 stages x ndof x 512 B per SM) and the hot loop has no LDG and
 // no address arithmetic.
 // ---------------------------------------------------------------------------------------------
+#ifndef SATMC_STREAMED_PACKED
+#define SATMC_STREAMED_PACKED 1
+#endif
 constexpr int kTile = 128;            // samples per tile per plane = 32 lanes x float4
 constexpr int kStages = 2;
 
@@ -623,12 +651,27 @@ k_count_streamed_tma(const __grid_constant__ DirectSrc src, const __grid_constan
             if (NDOF == 5) { d = tp[3 * (kTile / 4)]; e = tp[4 * (kTile / 4)]; }
             __syncwarp();                                             // every lane has its samples: the stage is free
             if (lane == 0 && t + kStages < n_tiles) issue(t + kStages);   // __syncwarp ordered the reads before this write
-            unsigned h0, h1, h2, h3;
-            bool ok = streamed_screen<NDOF>(P, a.x, b.x, c.x, d.x, e.x, h0);
-            ok = ok & streamed_screen<NDOF>(P, a.y, b.y, c.y, d.y, e.y, h1);
-            ok = ok & streamed_screen<NDOF>(P, a.z, b.z, c.z, d.z, e.z, h2);
-            ok = ok & streamed_screen<NDOF>(P, a.w, b.w, c.w, d.w, e.w, h3);
-            unsigned c4 = h0 + h1 + h2 + h3;
+            unsigned c4;
+            bool ok;
+            if (NDOF == 3 && SATMC_STREAMED_PACKED) {                  // two samples per packed-FP32 evaluation
+                float m0, m1, m2, m3;
+                screen_gap_pair3(P, a.x, b.x, c.x, a.y, b.y, c.y, m0, m1);
+                screen_gap_pair3(P, a.z, b.z, c.z, a.w, b.w, c.w, m2, m3);
+                c4 = (__float_as_uint(m0) >> 31) + (__float_as_uint(m1) >> 31) + (__float_as_uint(m2) >> 31) + (__float_as_uint(m3) >> 31);
+                // decided: every |m| above the threshold (NaN-propagating minimum) and every normal inside the bound
+                const float mn = min3_nan_abs(min3_nan_abs(CUDART_INF_F, m0, m1), m2, m3);
+                // largest |normal| of the four samples, NaN-propagating: "<= bound" is false for NaN, +-Inf exceeds it
+                const float zmax = max3_nan_abs(max3_nan_abs(max3_nan_abs(a.x, a.y, a.z), max3_nan_abs(a.w, b.x, b.y), max3_nan_abs(b.z, b.w, c.x)),
+                                                c.y, max3_nan_abs(c.z, c.w, 0.0f));
+                ok = (mn > P.eps) & (zmax <= SATMC_Z_BOUND);
+            } else {
+                unsigned h0, h1, h2, h3;
+                ok = streamed_screen<NDOF>(P, a.x, b.x, c.x, d.x, e.x, h0);
+                ok = ok & streamed_screen<NDOF>(P, a.y, b.y, c.y, d.y, e.y, h1);
+                ok = ok & streamed_screen<NDOF>(P, a.z, b.z, c.z, d.z, e.z, h2);
+                ok = ok & streamed_screen<NDOF>(P, a.w, b.w, c.w, d.w, e.w, h3);
+                c4 = h0 + h1 + h2 + h3;
+            }
             if (!ok) c4 = streamed_quad_slow<NDOF>(Pc, s_robot[warp], z, p.ldz, (uint64_t)t * kTile + 4 * lane, ev);
             cnt += c4;
         }

@@ -44,6 +44,8 @@ def classify(op: str, rest: str) -> str:
         return "IMAD(mov/shl/add)"
     if base in ("IMAD", "IMUL"):
         return "IMAD"
+    if base in ("FFMA2", "FMUL2", "FADD2"):
+        return "FP32x2"
     if base in ("FFMA", "FMUL", "FADD", "FMNMX", "FMNMX3", "FSETP", "FSEL", "FSET", "FCHK"):
         return "FP32"
     if base == "MUFU":
@@ -116,7 +118,7 @@ def summarise(instrs, s, e):
     text = "\n".join(op + re.sub(r"0x[0-9a-f]+", "X", rest) for _, op, rest in body)       # schedule and register assignment
     return {"start": hex(body[0][0]), "end": hex(body[-1][0]), "instr": len(body), "classes": dict(sorted(cnt.items())),
             "fingerprint": hashlib.sha1(text.encode()).hexdigest()[:16],
-            "imad_wide": cnt.get("IMAD.WIDE", 0), "fp32": cnt.get("FP32", 0), "mufu": cnt.get("MUFU", 0),
+            "imad_wide": cnt.get("IMAD.WIDE", 0), "fp32": cnt.get("FP32", 0), "fp32x2": cnt.get("FP32x2", 0), "mufu": cnt.get("MUFU", 0),
             "local_spill": cnt.get("LOCAL(spill)", 0),
             "opcodes": dict(sorted(ops.items(), key=lambda kv: -kv[1]))}
 
@@ -148,7 +150,7 @@ def main():
         report[nice] = entry
         print(f"== {nice}   ({len(instrs)} instructions)")
         for (s, e), L in zip(sorted(inner), entry["loops"]):
-            print(f"   loop {L['start']}..{L['end']}: {L['instr']} instr | IMAD.WIDE {L['imad_wide']} | FP32 {L['fp32']} | MUFU {L['mufu']} | "
+            print(f"   loop {L['start']}..{L['end']}: {L['instr']} instr | IMAD.WIDE {L['imad_wide']} | FP32 {L['fp32']} + {L['fp32x2']} packed | MUFU {L['mufu']} | "
                   f"spill ld/st {L['local_spill']}")
             print("      " + ", ".join(f"{k} {v}" for k, v in L["classes"].items()))
             if args.dump:
