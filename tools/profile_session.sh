@@ -10,10 +10,12 @@ nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,clocks.max.mem --format
 
 # 1. GPU test suite: shipped library, then the -DSATMC_DEBUG build (device-side bounds asserts)
 python -m pytest tests -m gpu -q 2>&1 | tail -6 > $O/${T}_gpu_suite.log
-( SATMC_LIB=$PWD/$P/debug/libsatmc.so LD_LIBRARY_PATH=$PWD/$P/debug python -m pytest tests -m gpu -q 2>&1 ) > $O/${T}_debug_full.log
+( SATMC_LIB=$PWD/$P/debug/libsatmc.so LD_LIBRARY_PATH=$PWD/$P/debug python -c "import importlib; m = importlib.import_module('$P'); print('library under test:', m.load_library().satmc_version().decode(), m.LIB_PATH)";
+  SATMC_LIB=$PWD/$P/debug/libsatmc.so LD_LIBRARY_PATH=$PWD/$P/debug python -m pytest tests -m gpu -q 2>&1 ) > $O/${T}_debug_full.log
 ( head -8 $O/${T}_debug_full.log; echo "..."; tail -6 $O/${T}_debug_full.log ) > $O/${T}_debug_suite.log; rm -f $O/${T}_debug_full.log
 
 # 2. bench lines
+python -c "import __graft_entry__ as g; g.smoke()" > $O/${T}_smoke.log 2>&1
 python bench.py > $O/${T}_bench_n1.json 2> $O/${T}_bench_n1.err
 python bench.py --impl reference --steps 5 --warmup 3 > $O/${T}_bench_reference_arm.json 2>> $O/${T}_bench_n1.err
 
