@@ -563,7 +563,10 @@ __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED
 #define SATMC_STREAMED_PACKED 1
 #endif
 constexpr int kTile = 128;            // samples per tile per plane = 32 lanes x float4
-constexpr int kStages = 2;
+#ifndef SATMC_TMA_STAGES
+#define SATMC_TMA_STAGES 2
+#endif
+constexpr int kStages = SATMC_TMA_STAGES;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
