@@ -117,6 +117,9 @@ int satmc_create(int device, void* stream, satmc_ctx** out)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_count<DirectSrc, true>, kThreads, 0);
     if (e != cudaSuccess || bps < 1) bps = SATMC_MIN_BLOCKS_STREAMED;
     ctx->blocks_per_sm_streamed = bps;
+    // dynamic shared memory beyond 48 KB is opt-in (deeper TMA rings)
+    if (tma_smem_bytes(3) > 48 * 1024) cudaFuncSetAttribute(k_count_streamed_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes(3));
+    if (tma_smem_bytes(5) > 48 * 1024) cudaFuncSetAttribute(k_count_streamed_tma<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes(5));
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_count_streamed_tma<3>, kThreads, tma_smem_bytes(3));
     ctx->blocks_per_sm_tma[0] = (e == cudaSuccess && bps >= 1) ? bps : 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_count_streamed_tma<5>, kThreads, tma_smem_bytes(5));
