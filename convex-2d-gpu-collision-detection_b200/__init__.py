@@ -443,9 +443,10 @@ class Group:
     def hits_capacity(self, n_pairs: int) -> int:
         return int(self._lib.satmc_group_hits_capacity(self._h, n_pairs))
 
-    def set_peer_reduce(self, on: bool) -> None:
-        """Allow / forbid the collective-free sample-range reduction over peer memory (count_fused_host, one process)."""
-        self._check(self._lib.satmc_group_set_peer_reduce(self._h, int(bool(on))))
+    def set_peer_reduce(self, on) -> None:
+        """Force on (True) / off (False) / automatic (None) the collective-free sample-range reduction over peer memory
+        (count_fused_host, one process)."""
+        self._check(self._lib.satmc_group_set_peer_reduce(self._h, -1 if on is None else int(bool(on))))
 
     def last_exchange(self) -> str:
         return {0: "none", 1: "nccl", 2: "peer_atomics"}[int(self._lib.satmc_group_last_exchange(self._h))]

@@ -302,8 +302,9 @@ int satmc_group_count_fused_host(satmc_group* g, const satmc_pair* h_pairs, uint
 /* How the last satmc_group_count_fused_host call combined the shards: nothing to combine (one device, or disjoint
  * slices read back directly), an NCCL collective, or -- sample ranges inside one process with few pairs -- no collective
  * at all: every device's counting kernel finishes into one counter array in device 0's memory with system-scope
- * atomics over NVLink (the reduction is the compute kernel's own epilogue).  satmc_group_set_peer_reduce(g, 0) forces
- * the NCCL path (for comparison); the counts are identical either way. */
+ * atomics over NVLink (the reduction is the compute kernel's own epilogue).  Chosen automatically from 6 devices on
+ * (measured per small call: 121 us against 147 us through NCCL at 8 GPUs, 89 against 80 at 4);
+ * satmc_group_set_peer_reduce(g, 1 / 0 / -1) forces it on / off / back to automatic.  Same counts either way. */
 #define SATMC_EXCHANGE_NONE          0
 #define SATMC_EXCHANGE_NCCL          1
 #define SATMC_EXCHANGE_PEER_ATOMICS  2

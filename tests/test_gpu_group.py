@@ -44,12 +44,16 @@ def test_group_counts_equal_single_gpu(ctx, dev, satmc, workloads, torch_cuda, w
         # sample ranges, few pairs, one process: the kernels finish into device 0's memory over NVLink (no collective);
         # with that path switched off the same call goes through ncclAllReduce -- same counts
         if world > 1:
+            assert g.last_exchange() == ("peer_atomics" if world >= 6 else "nccl")        # automatic choice
+            g.set_peer_reduce(True)
+            got = g.count_fused_host(pairs, n, seed, satmc.SHARD_BY_SAMPLE_RANGE, sample_offset=off, pair_id_offset=pid)
             assert g.last_exchange() == "peer_atomics"
+            np.testing.assert_array_equal(got, want, err_msg="host, sample ranges through peer atomics")
             g.set_peer_reduce(False)
             got = g.count_fused_host(pairs, n, seed, satmc.SHARD_BY_SAMPLE_RANGE, sample_offset=off, pair_id_offset=pid)
             assert g.last_exchange() == "nccl"
             np.testing.assert_array_equal(got, want, err_msg="host, sample ranges through NCCL")
-            g.set_peer_reduce(True)
+            g.set_peer_reduce(None)
         else:
             assert g.last_exchange() == "none"
         # resident inputs: the full pair array on every device, capacity-sized counters
@@ -79,6 +83,7 @@ def test_group_single_pair_cfg4_slice(ctx, dev, satmc, workloads, torch_cuda):
     one = workloads.cfg2_pair()
     want = fused(ctx, dev, one, 2_000_000_000, 4)
     with satmc.Group(devices=list(range(world))) as g:
+        g.set_peer_reduce(True)
         got = g.count_fused_host(one, 2_000_000_000, 4, satmc.SHARD_BY_SAMPLE_RANGE)
         assert g.last_exchange() == ("peer_atomics" if world > 1 else "none")
         g.set_peer_reduce(False)
