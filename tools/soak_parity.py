@@ -35,6 +35,28 @@ def poly_case(name, pp, n, seed):
     print(f"poly {name:28s} seed {seed:3d}: {pp.size * n:.2e} tests, to exact pass {ev / (pp.size * n):.3f}, mean p {h[0].sum().item() / (pp.size * n):.4f}, differing pairs {diff}", flush=True)
 
 
+def sweep_case(name, pairs, sig, n, seed):
+    global bad
+    d = put(pairs); h = [torch.zeros(pairs.size * sig.shape[0], dtype=torch.int64, device="cuda") for _ in range(2)]
+    ctx.exact_evals(reset=True)
+    ctx.count_fused_sweep(d, pairs.size, sig, sig.shape[0], n, seed, h[0]); ctx.synchronize(); ev = ctx.exact_evals(reset=True)
+    ctx.count_fused_sweep(d, pairs.size, sig, sig.shape[0], n, seed, h[1], flags=EXACT); ctx.synchronize()
+    diff = int((h[0] != h[1]).sum().item()); bad += diff
+    tests = pairs.size * sig.shape[0] * n
+    print(f"sweep {name:27s} seed {seed:3d}: {tests:.2e} tests, undecided {ev / tests:.2e}, mean p {h[0].sum().item() / tests:.4f}, differing rows {diff}", flush=True)
+
+
+def streamed_case(name, pairs, ndof, n, seed):
+    global bad
+    d = put(pairs); h = [torch.zeros(pairs.size, dtype=torch.int64, device="cuda") for _ in range(2)]
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    z = torch.randn(ndof * n, device="cuda", generator=g)
+    ctx.count_streamed(d, pairs.size, z, n, ndof, n, h[0]); ctx.synchronize()
+    ctx.count_streamed(d, pairs.size, z, n, ndof, n, h[1], flags=EXACT); ctx.synchronize()
+    diff = int((h[0] != h[1]).sum().item()); bad += diff
+    print(f"streamed {name:24s} seed {seed:3d}: {pairs.size * n:.2e} tests (shared bank, ndof {ndof}), mean p {h[0].sum().item() / (pairs.size * n):.4f}, differing pairs {diff}", flush=True)
+
+
 t0 = time.time()
 rng = np.random.default_rng(2026)
 for s in range(n_seeds):
@@ -57,5 +79,10 @@ for s in range(n_seeds):
     d = rng.uniform(0.0, 6.0, m); ang = rng.uniform(0, 2 * np.pi, m); sg = 10.0 ** rng.uniform(-2.5, -0.1, (3, m))
     pp = satmc.make_poly_pairs(robots, obstacles, d * np.cos(ang), d * np.sin(ang), rng.uniform(0, 6.28, m), sg[0], sg[1], sg[2])
     poly_case("random convex, mixed counts", pp, 100_000, 61 + s)
+    sig = np.sqrt(rng.uniform(0.0, 0.3, (64, 3))).astype(np.float32)
+    sig[:, 2] = rng.choice(np.sqrt(np.array([0.01, 0.05, 0.15, 0.3], np.float32)), 64)
+    sweep_case("64 settings, 4 theta levels", wl.dataset_pairs(2_000, seed=6000 + s), sig, 20_000, 71 + s)
+    streamed_case("dataset prior", wl.dataset_pairs(20_000, seed=7000 + s), 3, 100_000, 81 + s)
+    streamed_case("dataset prior, 5-DoF", wl.dataset_pairs(20_000, seed=7500 + s, shape_variance=True), 5, 50_000, 91 + s)
 print(f"total differing pairs {bad}; {time.time() - t0:.0f} s")
 sys.exit(1 if bad else 0)
