@@ -619,16 +619,18 @@ int satmc_group_adaptive_run_host(satmc_group* g, const float* h_pose_idxs, cons
         GSAT(g, l, satmc_adaptive_begin(ar));
     }
     // lockstep: one iteration on every device that still has live rows, then one synchronisation each
+    std::vector<char> busy(nl);
     for (;;) {
         bool any = false;
         for (size_t l = 0; l < nl; l++) {
-            if (!satmc_adaptive_pending(runs[l])) continue;
+            busy[l] = satmc_adaptive_pending(runs[l]) ? 1 : 0;
+            if (!busy[l]) continue;
             any = true;
             GSAT(g, l, satmc_adaptive_enqueue(runs[l]));
         }
         if (!any) break;
-        for (size_t l = 0; l < nl; l++) {
-            if (!satmc_adaptive_pending(runs[l])) continue;
+        for (size_t l = 0; l < nl; l++) {                              // (enqueue advanced n_samples: go by what was enqueued)
+            if (!busy[l]) continue;
             GCU(g, cudaSetDevice(g->dev[l].ctx->device));
             GCU(g, cudaStreamSynchronize(g->dev[l].stream));
             satmc_adaptive_collect(runs[l]);

@@ -93,9 +93,10 @@ def test_group_single_pair_cfg4_slice(ctx, dev, satmc, workloads, torch_cuda):
     assert abs(int(want[0]) / 2e9 - 0.166) < 0.01
 
 
-def adaptive_single(ctx, dev, workloads, pairs, max_samples, seed, stream_offset):
+def adaptive_single(ctx, dev, workloads, pairs, max_samples, seed, stream_offset, tight=False):
     rb, poses, sds, pi, si, pos = workloads.reference_tables(pairs)
-    bins = np.array([0, 0.01, 0.1, 1.0], np.float32); acc = np.array([1e-3, 3e-3, 1e-2], np.float32)
+    bins = np.array([0, 0.01, 0.1, 1.0], np.float32)
+    acc = np.array([1e-5, 1e-5, 1e-5], np.float32) if tight else np.array([1e-3, 3e-3, 1e-2], np.float32)
     d = [dev.put(a) for a in (rb, poses.ravel(), sds.ravel(), pi, si, pos.ravel(), bins, acc)]
     d_cp = dev.zeros(pairs.size, np.float32)
     it, drawn = ctx.adaptive_run(d[0], d[1], pairs.size, d[2], pairs.size, d[3], d[4], d[5], pairs.size, d[6], d[7], 4, max_samples,
@@ -118,6 +119,13 @@ def test_group_adaptive_rows_interleaved(ctx, dev, satmc, workloads, torch_cuda,
     np.testing.assert_array_equal(cp, want)
     assert drawn == drawn1 and it == it1
     assert 0 < (want > 0).mean() < 1
+    # the same with a budget that stops the loop before every row is done (the leftovers are finalised as they stand)
+    want2, it2, drawn2, _ = adaptive_single(ctx, dev, workloads, pairs, 25_000, 9, 1000, tight=True)
+    with satmc.Group(devices=list(range(world))) as g:
+        g.set_tables(rb, poses, sds, bins, np.array([1e-5, 1e-5, 1e-5], np.float32))
+        cp2, it_g, drawn_g = g.adaptive_run_host(pi, si, pos, 25_000, 1000, 20000, 100000, 9, stream_id_offset=1000)
+    np.testing.assert_array_equal(cp2, want2)
+    assert it_g == it2 and drawn_g == drawn2
 
 
 def test_single_launch_counters_leave_no_state_behind(ctx, dev, oracle, workloads):
