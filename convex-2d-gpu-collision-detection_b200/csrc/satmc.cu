@@ -117,9 +117,9 @@ int satmc_create(int device, void* stream, satmc_ctx** out)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_count<DirectSrc, true>, kThreads, 0);
     if (e != cudaSuccess || bps < 1) bps = SATMC_MIN_BLOCKS_STREAMED;
     ctx->blocks_per_sm_streamed = bps;
-    // dynamic shared memory beyond 48 KB is opt-in (deeper TMA rings)
-    if (tma_smem_bytes(3) > 48 * 1024) cudaFuncSetAttribute(k_count_streamed_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes(3));
-    if (tma_smem_bytes(5) > 48 * 1024) cudaFuncSetAttribute(k_count_streamed_tma<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes(5));
+    // dynamic + static shared memory beyond 48 KB is opt-in (deeper TMA rings, larger tiles)
+    if (tma_smem_bytes(3) > 40 * 1024) cudaFuncSetAttribute(k_count_streamed_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes(3));
+    if (tma_smem_bytes(5) > 40 * 1024) cudaFuncSetAttribute(k_count_streamed_tma<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes(5));
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_count_streamed_tma<3>, kThreads, tma_smem_bytes(3));
     ctx->blocks_per_sm_tma[0] = (e == cudaSuccess && bps >= 1) ? bps : 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_count_streamed_tma<5>, kThreads, tma_smem_bytes(5));
@@ -138,6 +138,8 @@ int satmc_create(int device, void* stream, satmc_ctx** out)
     ctx->d_blocks_done = reinterpret_cast<unsigned*>(ctx->d_ticket + 2);
     // development knobs (multiples of 128 samples)
     if (const char* e = getenv("SATMC_MIN_CHUNK")) { const long v = atol(e); if (v >= 128) ctx->tune_min_chunk = (uint64_t)v / 128 * 128; }
+    if (const char* e = getenv("SATMC_STREAM_CHUNK")) { const long v = atol(e); if (v >= 256) ctx->tune_stream_chunk = (uint64_t)v / 256 * 256; }
+    if (const char* e = getenv("SATMC_STREAM_IPW")) { const long v = atol(e); if (v >= 1 && v <= 4096) ctx->tune_stream_ipw = (int)v; }
     if (const char* e = getenv("SATMC_TINY_CHUNK")) { const long v = atol(e); if (v >= 128) ctx->tune_tiny_chunk = (uint64_t)v / 128 * 128; }
     *out = ctx;
     return SATMC_OK;
@@ -289,12 +291,16 @@ static void use_tickets(satmc_ctx* ctx, CountParams& p, uint64_t blocks)
 // totals to the caller's array (or adds them, SATMC_ACCUMULATE) and zeroes the scratch again (finalize_counters).
 // `span` = counters behind p.hits, of which this launch owns `counters`, laid out as fin_inner consecutive ones every
 // fin_stride.
-static int prepare_counters(satmc_ctx* ctx, CountParams& p, uint64_t span, uint64_t counters, uint64_t fin_inner = 1,
+// `arrivals` = contributions every counter receives when that number is the same for all of them (0: irregular, e.g.
+// the deferred queue): the packed scheme of packed_arrive then finishes each counter with its last contribution and
+// the kernel needs no tail; it is kept only if the counts fit the packing (else p.arrivals stays 0: tail pass).
+static int prepare_counters(satmc_ctx* ctx, CountParams& p, uint64_t span, uint64_t counters, uint32_t arrivals, uint64_t fin_inner = 1,
                             uint64_t fin_stride = 1, uint64_t acc_offset = 0)
 {
     p.hits_len = span - acc_offset;
-    p.acc = nullptr; p.blocks_done = nullptr;
+    p.acc = nullptr; p.blocks_done = nullptr; p.arrivals = 0;
     if (p.n_chunks <= 1) return SATMC_OK;
+    if (arrivals < (1u << 24) && p.chunk * (uint64_t)p.n_chunks < (1ull << kPackShift)) p.arrivals = arrivals;
     const int sel = ctx->ticket_sel;
     if (span > ctx->acc_cap[sel]) {
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -339,14 +345,13 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
     // off 32 at a time (ColdQueue, k_count<.., DEFER = true>).  Items are capped at 2^20 samples so that the queue holds an
     // item's undecided groups at the rates seen in practice (<= 2.4e-4 per test).  Short items keep the immediate path:
     // there the queue's bookkeeping costs more than the few undecided groups of an item.
-    int rc = plan_items(ctx, p, bps, blocks, 8, STREAMED ? (1ull << 36) : (1ull << 20));
+    int rc = plan_items(ctx, p, bps, blocks, tma ? ctx->tune_stream_ipw : 8, tma ? ctx->tune_stream_chunk : (STREAMED ? (1ull << 36) : (1ull << 20)));
     if (rc) return rc;
     const bool defer = !STREAMED && p.chunk >= 32768;
-    rc = prepare_counters(ctx, p, p.n_pairs, p.n_pairs);
+    // without the deferred queue every counter receives a known number of contributions (packed_arrive)
+    rc = prepare_counters(ctx, p, p.n_pairs, p.n_pairs, defer ? 0u : (p.block_uniform ? p.n_chunks / kWarps : p.n_chunks));
     if (rc) return rc;
-    // k_count without the deferred queue: every counter receives a known number of contributions (packed_arrive)
-    p.arrivals = p.block_uniform ? p.n_chunks / kWarps : p.n_chunks;
-    if (p.acc && !defer && !tma && (p.n_chunks >= (1u << 24) || p.chunk * (uint64_t)p.n_chunks >= (1ull << kPackShift)))
+    if (p.acc && !defer && !tma && p.arrivals == 0u)                  // (k_count's packed scheme is a template parameter)
         return fail(ctx, SATMC_ERR_INVALID, "sample range too long for one call (%llu samples per pair)", (unsigned long long)p.n_samples);
     const uint64_t ticket_before = ctx->ticket_next[ctx->ticket_sel];
     // bulk-copy staged kernel: dynamic order only when all pairs read one shared bank (L2 resident, issue bound: +5 %);
@@ -535,7 +540,7 @@ int satmc_count_fused_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs, u
     uint64_t blocks = 0;
     int rc = plan_items(ctx, p, 2, blocks);
     if (rc) return rc;
-    rc = prepare_counters(ctx, p, n_pairs, n_pairs);
+    rc = prepare_counters(ctx, p, n_pairs, n_pairs, p.block_uniform ? p.n_chunks / kWarps : p.n_chunks);
     if (rc) return rc;
     const uint64_t ticket_before = ctx->ticket_next[ctx->ticket_sel];
     use_tickets(ctx, p, blocks);
@@ -563,7 +568,7 @@ int satmc_count_streamed_polygons(satmc_ctx* ctx, const satmc_poly_pair* d_pairs
     uint64_t blocks = 0;
     rc = plan_items(ctx, p, 2, blocks);
     if (rc) return rc;
-    rc = prepare_counters(ctx, p, n_pairs, n_pairs);
+    rc = prepare_counters(ctx, p, n_pairs, n_pairs, p.block_uniform ? p.n_chunks / kWarps : p.n_chunks);
     if (rc) return rc;
     const uint64_t ticket_before = ctx->ticket_next[ctx->ticket_sel];
     use_tickets(ctx, p, blocks);
@@ -615,7 +620,7 @@ int satmc_count_fused_sweep(satmc_ctx* ctx, const satmc_pair* d_pairs, uint64_t 
         }
         CountParams q = p;
         q.hits = p.hits + c0;
-        rc = prepare_counters(ctx, q, n_pairs * n_cov, n_pairs * (uint64_t)nc, (uint64_t)nc, (uint64_t)n_cov, c0);
+        rc = prepare_counters(ctx, q, n_pairs * n_cov, n_pairs * (uint64_t)nc, q.n_chunks, (uint64_t)nc, (uint64_t)n_cov, c0);
         if (rc) return rc;
         k_count_sweep<SATMC_SWEEP_G><<<(unsigned)blocks, 32 * kSweepWarps, 0, ctx->stream>>>(d_pairs, W, (uint64_t)n_cov, q);
         CU(ctx, cudaGetLastError());

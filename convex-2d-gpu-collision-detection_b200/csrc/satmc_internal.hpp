@@ -40,6 +40,8 @@ struct satmc_ctx {
     unsigned* d_blocks_done = nullptr;
     int* h_word = nullptr;                   // pinned: the adaptive loop's "pairs left" comes back here
     uint64_t tune_min_chunk = 2048, tune_tiny_chunk = 256;   // planner: samples per work item (see plan_items)
+    uint64_t tune_stream_chunk = 1ull << 36;                 // planner: most samples per work item, streamed bulk-tensor path
+    int tune_stream_ipw = 8;                                 // planner: work items per resident warp, streamed bulk-tensor path
 };
 
 // State of one adaptive z-test loop (satmc_adaptive_run) on one context, in steps: begin, then while pending

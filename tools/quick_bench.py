@@ -40,6 +40,8 @@ def main():
     print(torch.cuda.get_device_name(0))
     flags = [0] + ([satmc.SATMC_EXACT_ONLY] if "--exact" in sys.argv else [])
     if "--only" in sys.argv:
+        if "--streamed" in sys.argv:
+            streamed_part(ctx)
         return rest_part(ctx)
     cases = (("cfg3 1e5x1e4", wl.dataset_pairs(100_000, 3), 10_000),
                            ("cfg3 5dof 1e5x1e4", wl.dataset_pairs(100_000, 3, shape_variance=True), 10_000),
@@ -76,11 +78,13 @@ def streamed_part(ctx):
         print(f"streamed shared-bank ndof={ndof} {pairs.size}x{n}: best {best:.3f} ms {pairs.size * n / best / 1e6:.2f} Gtests/s")
     for ndof in (3, 5):
         npairs, n = 16384, 32768
+        torch.manual_seed(ndof)
         z = torch.randn(ndof * npairs * n, device="cuda")          # 6.4 / 10.7 GB
         pp = wl.dataset_pairs(npairs, 9); d_pp = put(pp); d_h = torch.zeros(npairs, dtype=torch.int64, device="cuda")
         best, med = time_call(lambda: ctx.count_streamed(d_pp, npairs, z, npairs * n, ndof, n, d_h, z_pair_stride=n))
         gb = ndof * 4 * npairs * n / 1e9
-        print(f"streamed private ndof={ndof} {npairs}x{n}: best {best:.3f} ms {npairs * n / best / 1e6:.2f} Gtests/s  {gb / best * 1e3:.1f} GB/s")
+        print(f"streamed private ndof={ndof} {npairs}x{n}: best {best:.3f} ms {npairs * n / best / 1e6:.2f} Gtests/s  {gb / best * 1e3:.1f} GB/s"
+              f"  hits {d_h.sum().item()}")
         del z
 
 
