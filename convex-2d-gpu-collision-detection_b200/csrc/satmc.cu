@@ -26,7 +26,7 @@ char* satmc_thread_error()
     return e;
 }
 
-static inline size_t tma_smem_bytes(int ndof) { return (size_t)kWarps * kStages * ndof * kTile * sizeof(float); }
+static inline size_t tma_smem_bytes(int ndof, bool shared_bank) { return (size_t)kWarps * tma_stages(ndof) * ndof * tma_tile(ndof, shared_bank) * sizeof(float); }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
 typedef CUresult (*tensor_map_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -49,13 +49,13 @@ static tensor_map_encode_fn get_tensor_map_encode()
 }
 
 // 2-D tensor [ndof][ldz] of float32 over the sample bank, box = [ndof][kTile]
-static bool make_z_tensor_map(CUtensorMap* map, const float* z, uint64_t ldz, int ndof)
+static bool make_z_tensor_map(CUtensorMap* map, const float* z, uint64_t ldz, int ndof, int tile)
 {
     tensor_map_encode_fn enc = get_tensor_map_encode();
     if (!enc) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)ldz, (cuuint64_t)ndof};
     const cuuint64_t strides[1] = {(cuuint64_t)ldz * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)kTile, (cuuint32_t)ndof};
+    const cuuint32_t box[2] = {(cuuint32_t)tile, (cuuint32_t)ndof};
     const cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(z), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -118,12 +118,17 @@ int satmc_create(int device, void* stream, satmc_ctx** out)
     if (e != cudaSuccess || bps < 1) bps = SATMC_MIN_BLOCKS_STREAMED;
     ctx->blocks_per_sm_streamed = bps;
     // dynamic + static shared memory beyond 48 KB is opt-in (deeper TMA rings, larger tiles)
-    if (tma_smem_bytes(3) > 40 * 1024) cudaFuncSetAttribute(k_count_streamed_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes(3));
-    if (tma_smem_bytes(5) > 40 * 1024) cudaFuncSetAttribute(k_count_streamed_tma<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes(5));
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_count_streamed_tma<3>, kThreads, tma_smem_bytes(3));
-    ctx->blocks_per_sm_tma[0] = (e == cudaSuccess && bps >= 1) ? bps : 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_count_streamed_tma<5>, kThreads, tma_smem_bytes(5));
-    ctx->blocks_per_sm_tma[1] = (e == cudaSuccess && bps >= 1) ? bps : 1;
+    auto tma_setup = [&](auto kernel, int ndof, bool shared_bank, int& out) {
+        const size_t bytes = tma_smem_bytes(ndof, shared_bank);
+        if (bytes > 40 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        int n = 0;
+        const cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, bytes);
+        out = (err == cudaSuccess && n >= 1) ? n : 1;
+    };
+    tma_setup(k_count_streamed_tma<3, tma_tile(3, false)>, 3, false, ctx->blocks_per_sm_tma[0][0]);
+    tma_setup(k_count_streamed_tma<3, tma_tile(3, true)>, 3, true, ctx->blocks_per_sm_tma[0][1]);
+    tma_setup(k_count_streamed_tma<5, tma_tile(5, false)>, 5, false, ctx->blocks_per_sm_tma[1][0]);
+    tma_setup(k_count_streamed_tma<5, tma_tile(5, true)>, 5, true, ctx->blocks_per_sm_tma[1][1]);
     cudaGetLastError();
     if (cudaMalloc(&ctx->d_exact_evals, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(ctx->d_exact_evals, 0, sizeof(unsigned long long)) != cudaSuccess ||
@@ -138,7 +143,8 @@ int satmc_create(int device, void* stream, satmc_ctx** out)
     ctx->d_blocks_done = reinterpret_cast<unsigned*>(ctx->d_ticket + 2);
     // development knobs (multiples of 128 samples)
     if (const char* e = getenv("SATMC_MIN_CHUNK")) { const long v = atol(e); if (v >= 128) ctx->tune_min_chunk = (uint64_t)v / 128 * 128; }
-    if (const char* e = getenv("SATMC_STREAM_CHUNK")) { const long v = atol(e); if (v >= 256) ctx->tune_stream_chunk = (uint64_t)v / 256 * 256; }
+    if (const char* e = getenv("SATMC_STREAM_CHUNK3")) { const long v = atol(e); if (v >= 256) ctx->tune_stream_chunk[0] = (uint64_t)v / 256 * 256; }
+    if (const char* e = getenv("SATMC_STREAM_CHUNK5")) { const long v = atol(e); if (v >= 256) ctx->tune_stream_chunk[1] = (uint64_t)v / 256 * 256; }
     if (const char* e = getenv("SATMC_STREAM_IPW")) { const long v = atol(e); if (v >= 1 && v <= 4096) ctx->tune_stream_ipw = (int)v; }
     if (const char* e = getenv("SATMC_TINY_CHUNK")) { const long v = atol(e); if (v >= 128) ctx->tune_tiny_chunk = (uint64_t)v / 128 * 128; }
     *out = ctx;
@@ -215,7 +221,8 @@ int satmc_exact_evals(satmc_ctx* ctx, uint64_t* out, int reset)
 // REDUX warp total, the sweep's per-setting shared-memory counters), so no item may exceed 2^31 samples.
 constexpr uint64_t kMaxChunk = 1ull << 31;
 static int plan_items(satmc_ctx* ctx, CountParams& p, int bps, uint64_t& blocks, int items_per_warp = 8,
-                      uint64_t max_chunk = kMaxChunk, int warps_per_block = kWarps)
+                      uint64_t max_chunk = kMaxChunk, int warps_per_block = kWarps, uint64_t granule = 128,
+                      bool block_sums = true)
 {
     const uint64_t kWarps = (uint64_t)warps_per_block;                // (shadows the default block shape)
     const uint64_t resident_warps = (uint64_t)ctx->sm_count * bps * kWarps;
@@ -238,16 +245,16 @@ static int plan_items(satmc_ctx* ctx, CountParams& p, int bps, uint64_t& blocks,
     if (max_chunk > kMaxChunk) max_chunk = kMaxChunk;
     const uint64_t per_chunk = (p.n_samples + n_chunks - 1) / n_chunks;
     if (per_chunk > max_chunk) n_chunks *= (per_chunk + max_chunk - 1) / max_chunk;   // a multiple: the rounds stay full
-    if (n_chunks >= (uint64_t)kWarps) n_chunks = (n_chunks / kWarps) * kWarps;    // block-uniform pairs
+    if (block_sums && n_chunks >= (uint64_t)kWarps) n_chunks = (n_chunks / kWarps) * kWarps;    // block-uniform pairs
     uint64_t chunk = (p.n_samples + n_chunks - 1) / n_chunks;
-    chunk = ((chunk + 127) / 128) * 128;
-    if (chunk > kMaxChunk) chunk = kMaxChunk;                         // (a multiple of 128)
+    chunk = ((chunk + granule - 1) / granule) * granule;          // whole sample groups / whole bulk-tensor tiles
+    if (chunk > kMaxChunk) chunk = kMaxChunk;                         // (a multiple of 128 and of 256)
     n_chunks = (p.n_samples + chunk - 1) / chunk;
     if (n_chunks > 0xffffffffull) return fail(ctx, SATMC_ERR_INVALID, "too many chunks");
     p.chunk = chunk;
     p.n_chunks = (uint32_t)n_chunks;
     p.n_items = p.n_pairs * n_chunks;
-    p.block_uniform = (n_chunks % kWarps == 0) ? 1u : 0u;
+    p.block_uniform = (block_sums && n_chunks % kWarps == 0) ? 1u : 0u;
     blocks = (p.n_items + kWarps - 1) / kWarps;
     const uint64_t max_blocks = (uint64_t)ctx->sm_count * bps;
     if (blocks > max_blocks) blocks = max_blocks;
@@ -337,17 +344,27 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
     }
     // bulk-tensor path: aligned bank, coordinates that fit the TMA's 32-bit signed indices, a driver that encodes the map
     CUtensorMap zmap;
-    bool tma = STREAMED && p.vec_ok && p.ldz < (1ull << 31) && p.ldz >= (uint64_t)kTile;
-    if (tma) tma = make_z_tensor_map(&zmap, p.z, p.ldz, p.ndof);
-    const int bps = tma ? ctx->blocks_per_sm_tma[p.ndof == 5] : (STREAMED ? ctx->blocks_per_sm_streamed : ctx->blocks_per_sm);
+    const bool shared_bank = STREAMED && p.z_pair_stride == 0;        // every pair reads the same samples (common random numbers)
+    const int tile = tma_tile((int)p.ndof, shared_bank);
+    bool tma = STREAMED && p.vec_ok && p.ldz < (1ull << 31) && p.ldz >= (uint64_t)tile;
+    if (tma) tma = make_z_tensor_map(&zmap, p.z, p.ldz, p.ndof, tile);
+    const int bps = tma ? ctx->blocks_per_sm_tma[p.ndof == 5][shared_bank] : (STREAMED ? ctx->blocks_per_sm_streamed : ctx->blocks_per_sm);
     uint64_t blocks = 0;
     // Long items (few pairs, many samples each -- cfg 4, cfg 5): undecided sample groups are queued per warp and worked
     // off 32 at a time (ColdQueue, k_count<.., DEFER = true>).  Items are capped at 2^20 samples so that the queue holds an
     // item's undecided groups at the rates seen in practice (<= 2.4e-4 per test).  Short items keep the immediate path:
     // there the queue's bookkeeping costs more than the few undecided groups of an item.
-    int rc = plan_items(ctx, p, bps, blocks, tma ? ctx->tune_stream_ipw : 8, tma ? ctx->tune_stream_chunk : (STREAMED ? (1ull << 36) : (1ull << 20)));
+    // Bulk-tensor kernel on private banks (HBM bound): short items keep the addresses the resident warps stream from
+    // close together; the ring runs across items, so a switch costs only the pair prologue.  Measured on five bank
+    // shapes (profiles/r2_streamed_ring_experiments.log): 3-DoF 6.0-6.3 -> 6.6-6.8 TB/s with items of 2048 samples,
+    // 5-DoF 6.6-6.9 -> 6.8-6.95 TB/s with 8192.  A shared (L2-resident) bank is issue bound: items stay long.
+    uint64_t max_chunk = STREAMED ? (1ull << 36) : (1ull << 20);
+    if (tma && !shared_bank) max_chunk = ctx->tune_stream_chunk[p.ndof == 5];
+    int rc = plan_items(ctx, p, bps, blocks, tma ? ctx->tune_stream_ipw : 8, max_chunk, kWarps, tma ? (uint64_t)tile : 128, !tma);
     if (rc) return rc;
     const bool defer = !STREAMED && p.chunk >= 32768;
+    // (the bulk-tensor kernel's warps never meet at a block barrier -- block_sums = false above: one packed atomic per
+    // item is cheap, a barrier per item keeps eight private rings in lockstep)
     // without the deferred queue every counter receives a known number of contributions (packed_arrive)
     rc = prepare_counters(ctx, p, p.n_pairs, p.n_pairs, defer ? 0u : (p.block_uniform ? p.n_chunks / kWarps : p.n_chunks));
     if (rc) return rc;
@@ -359,10 +376,12 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
     if (!tma || p.z_pair_stride == 0) use_tickets(ctx, p, blocks);
     if (time_it && !ctx->events_by_caller) CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if constexpr (STREAMED) {
-        if (tma && p.ndof == 5)
-            k_count_streamed_tma<5><<<(unsigned)blocks, kThreads, tma_smem_bytes(5), ctx->stream>>>(src, p, zmap);
+        if (tma && p.ndof == 5) {
+            if (shared_bank) k_count_streamed_tma<5, tma_tile(5, true)><<<(unsigned)blocks, kThreads, tma_smem_bytes(5, true), ctx->stream>>>(src, p, zmap);
+            else k_count_streamed_tma<5, tma_tile(5, false)><<<(unsigned)blocks, kThreads, tma_smem_bytes(5, false), ctx->stream>>>(src, p, zmap);
+        }
         else if (tma)
-            k_count_streamed_tma<3><<<(unsigned)blocks, kThreads, tma_smem_bytes(3), ctx->stream>>>(src, p, zmap);
+            k_count_streamed_tma<3, tma_tile(3, false)><<<(unsigned)blocks, kThreads, tma_smem_bytes(3, shared_bank), ctx->stream>>>(src, p, zmap);
         else
             if (p.acc) k_count<Src, true, false, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);
             else k_count<Src, true, false, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(src, p);

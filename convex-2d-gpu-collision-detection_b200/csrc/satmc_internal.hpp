@@ -13,7 +13,7 @@ struct satmc_ctx {
     int sm_count = 0;
     int blocks_per_sm = 0;
     int blocks_per_sm_streamed = 0;
-    int blocks_per_sm_tma[2] = {0, 0};       // bulk-copy staged streamed kernel, ndof 3 / 5
+    int blocks_per_sm_tma[2][2] = {{0, 0}, {0, 0}};   // bulk-copy staged streamed kernel, [ndof 3 / 5][private / shared bank]
     char err[512] = {0};
     uint64_t launches = 0;
     unsigned long long* d_exact_evals = nullptr;
@@ -40,7 +40,7 @@ struct satmc_ctx {
     unsigned* d_blocks_done = nullptr;
     int* h_word = nullptr;                   // pinned: the adaptive loop's "pairs left" comes back here
     uint64_t tune_min_chunk = 2048, tune_tiny_chunk = 256;   // planner: samples per work item (see plan_items)
-    uint64_t tune_stream_chunk = 1ull << 36;                 // planner: most samples per work item, streamed bulk-tensor path
+    uint64_t tune_stream_chunk[2] = {2048, 8192};            // planner: most samples per work item, bulk-tensor path on private banks (3-DoF, 5-DoF)
     int tune_stream_ipw = 8;                                 // planner: work items per resident warp, streamed bulk-tensor path
 };
 

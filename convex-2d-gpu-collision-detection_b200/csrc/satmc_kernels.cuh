@@ -33,7 +33,7 @@ constexpr int kWarps = kThreads / 32;
 #endif
 // bulk-tensor streamed kernel (measured: 3-DoF 5.58 / 5.73 / 5.26 TB/s, 5-DoF 6.62 / 5.88 / 5.74 TB/s at 2 / 3 / 4 blocks)
 #ifndef SATMC_MIN_BLOCKS_TMA3
-#define SATMC_MIN_BLOCKS_TMA3 3
+#define SATMC_MIN_BLOCKS_TMA3 2
 #endif
 #ifndef SATMC_MIN_BLOCKS_TMA5
 #define SATMC_MIN_BLOCKS_TMA5 2
@@ -583,15 +583,32 @@ __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED
 #ifndef SATMC_STREAMED_PACKED
 #define SATMC_STREAMED_PACKED 1
 #endif
-#ifndef SATMC_TMA_TILE
-#define SATMC_TMA_TILE 128
+// Ring geometry per sample layout and bank kind (measured on B200, profiles/r2_streamed_ring_experiments.log), all at
+// 2 blocks per SM.  The 3-DoF loop is short (45 instructions per test), so the per-tile bookkeeping and the bytes in
+// flight per warp decide: 4 stages of 256 samples (no spills at 128 registers).  The 5-DoF loop streams private banks
+// from HBM best with 2 stages of 128 samples (6.9 vs 6.4 TB/s with 256), while on a shared, L2-resident bank it is
+// issue bound and 256-sample tiles halve the per-tile bookkeeping (526 vs 465 Gtests/s).
+#ifndef SATMC_TMA_TILE3
+#define SATMC_TMA_TILE3 256
 #endif
-constexpr int kTile = SATMC_TMA_TILE; // samples per tile per plane: kTile / 128 sub-tiles of 32 lanes x float4
-static_assert(kTile % 128 == 0 && kTile <= 256, "a bulk-tensor box row is at most 256 elements");
-#ifndef SATMC_TMA_STAGES
-#define SATMC_TMA_STAGES 2
+#ifndef SATMC_TMA_STAGES3
+#define SATMC_TMA_STAGES3 4
 #endif
-constexpr int kStages = SATMC_TMA_STAGES;
+#ifndef SATMC_TMA_TILE5
+#define SATMC_TMA_TILE5 128
+#endif
+#ifndef SATMC_TMA_TILE5_SHARED
+#define SATMC_TMA_TILE5_SHARED 256
+#endif
+#ifndef SATMC_TMA_STAGES5
+#define SATMC_TMA_STAGES5 2
+#endif
+// samples per tile per plane (tile / 128 sub-tiles of 32 lanes x float4) and ring depth
+__host__ __device__ constexpr int tma_tile(int ndof, bool shared_bank) { return ndof == 5 ? (shared_bank ? SATMC_TMA_TILE5_SHARED : SATMC_TMA_TILE5) : SATMC_TMA_TILE3; }
+__host__ __device__ constexpr int tma_stages(int ndof) { return ndof == 5 ? SATMC_TMA_STAGES5 : SATMC_TMA_STAGES3; }
+static_assert(tma_tile(3, false) % 128 == 0 && tma_tile(3, false) <= 256 && tma_tile(5, false) % 128 == 0 && tma_tile(5, false) <= 256 &&
+              tma_tile(5, true) % 128 == 0 && tma_tile(5, true) <= 256, "a bulk-tensor box row is at most 256 elements");
+static_assert((tma_stages(3) & (tma_stages(3) - 1)) == 0 && (tma_stages(5) & (tma_stages(5) - 1)) == 0, "ring depth: a power of two");
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -617,11 +634,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
                  :: "r"(smem_addr(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_addr(bar)) : "memory");
 }
 
-template <int NDOF>
+template <int NDOF, int kTile>
 __global__ void __launch_bounds__(kThreads, NDOF == 5 ? SATMC_MIN_BLOCKS_TMA5 : SATMC_MIN_BLOCKS_TMA3)
 k_count_streamed_tma(const __grid_constant__ DirectSrc src, const __grid_constant__ CountParams p,
                      const __grid_constant__ CUtensorMap zmap)
 {
+    constexpr int kStages = tma_stages(NDOF);
     extern __shared__ __align__(128) float s_tiles[];                 // [kWarps][kStages][NDOF][kTile]
     __shared__ __align__(8) uint64_t s_bar[kWarps][kStages];
     __shared__ float s_robot[kWarps][8];
@@ -637,10 +655,53 @@ k_count_streamed_tma(const __grid_constant__ DirectSrc src, const __grid_constan
     __syncwarp();
     uint32_t tiles_done = 0;                                          // running tile counter: stage and parity
     const uint64_t stride = (uint64_t)gridDim.x * kWarps;
+    // The ring runs across work items: while a warp consumes the last tiles of an item, lane 0 already requests the
+    // first tiles of the warp's next item, so an item switch costs no memory round trip and items can be short (a
+    // short item keeps the addresses the resident warps stream from close together).  Lane 0 only:
+    int nx_x0 = 0;                                                    // tensor coordinate of the next item's chunk
+    uint32_t nx_tiles = 0;                                            // its whole tiles
+    bool nx_known = false;
+    uint32_t pre = 0;                                                 // tiles of the CURRENT item requested while the previous one ran
     for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < p.n_items;) {
         const unsigned long long drawn = draw_ticket(p, lane);
         const uint64_t pair = item / p.n_chunks;
         const uint32_t chunk_id = (uint32_t)(item - pair * p.n_chunks);
+        const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
+        const uint64_t c_len = (c_begin + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - c_begin);
+        const uint32_t n_tiles = (uint32_t)(c_len / kTile);
+        const int x0 = (int)(pair * p.z_pair_stride + c_begin);       // tensor coordinate of the chunk (< 2^31, host-checked)
+        // request number u of this item's stream: its own tile u, or tile u - n_tiles of the warp's next item
+        auto issue = [&](uint32_t u) {                                // lane 0 only
+            int x;
+            if (u < n_tiles) {
+                x = x0 + (int)(u * kTile);
+            } else {
+                if (!nx_known) {
+                    const uint64_t nx = (p.ticket != nullptr ? (uint64_t)(drawn - p.ticket_base) : item) + stride;
+                    nx_tiles = 0;
+                    if (nx < p.n_items) {
+                        const uint64_t npair = nx / p.n_chunks;
+                        const uint64_t nb = (nx - npair * p.n_chunks) * p.chunk;
+                        const uint64_t nl = (nb + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - nb);
+                        nx_tiles = (uint32_t)(nl / kTile);
+                        nx_x0 = (int)(npair * p.z_pair_stride + nb);
+                    }
+                    nx_known = true;
+                }
+                const uint32_t w = u - n_tiles;
+                if (w >= nx_tiles) return;                            // (no look-ahead beyond the next item)
+                x = nx_x0 + (int)(w * kTile);
+                pre = w + 1;
+            }
+            const uint32_t st = (tiles_done + u) % kStages;
+            mbar_expect_tx(&s_bar[warp][st], NDOF * kTile * 4);
+            tma_load_2d(my_tiles + (size_t)st * NDOF * kTile, &zmap, x, 0, &s_bar[warp][st]);
+        };
+        if (lane == 0) {
+            const uint32_t have = pre;
+            pre = 0; nx_known = false;
+            for (uint32_t u = have; u < (uint32_t)kStages; u++) issue(u);
+        }
         float v[12];
         src.load(pair, v);
         PairConst P;
@@ -655,20 +716,9 @@ k_count_streamed_tma(const __grid_constant__ DirectSrc src, const __grid_constan
         }
         __syncwarp();
         const PairConst& Pc = s_pair[warp];
-        const uint64_t c_begin = (uint64_t)chunk_id * p.chunk;
-        const uint64_t c_len = (c_begin + p.chunk <= p.n_samples) ? p.chunk : (p.n_samples - c_begin);
         unsigned long long* ev = (p.flags & SATMC_EXACT_ONLY) ? nullptr : p.exact_evals;
         SATMC_ASSERT(pair < p.hits_len && c_begin < p.n_samples);
         const float* z = p.z + pair * p.z_pair_stride + c_begin;
-        const uint32_t n_tiles = (uint32_t)(c_len / kTile);
-        const int x0 = (int)(pair * p.z_pair_stride + c_begin);       // tensor coordinate of the chunk (< 2^31, host-checked)
-        auto issue = [&](uint32_t t) {                                // lane 0 only
-            const uint32_t st = (tiles_done + t) % kStages;
-            mbar_expect_tx(&s_bar[warp][st], NDOF * kTile * 4);
-            tma_load_2d(my_tiles + (size_t)st * NDOF * kTile, &zmap, x0 + (int)(t * kTile), 0, &s_bar[warp][st]);
-        };
-        if (lane == 0)
-            for (uint32_t t = 0; t < n_tiles && t < (uint32_t)kStages; t++) issue(t);
         unsigned cnt = 0;
         for (uint32_t t = 0; t < n_tiles; t++) {
             const uint32_t seq = tiles_done + t, st = seq % kStages;
@@ -681,7 +731,7 @@ k_count_streamed_tma(const __grid_constant__ DirectSrc src, const __grid_constan
                 if (NDOF == 5) { d = tp[3 * (kTile / 4)]; e = tp[4 * (kTile / 4)]; }
                 if (sub == kTile / 128 - 1) {
                     __syncwarp();                                         // every lane has its samples: the stage is free
-                    if (lane == 0 && t + kStages < n_tiles) issue(t + kStages);   // __syncwarp ordered the reads before this write
+                    if (lane == 0) issue(t + kStages);                // __syncwarp ordered the reads before this write
                 }
                 unsigned c4;
                 bool ok;

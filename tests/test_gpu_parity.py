@@ -163,6 +163,20 @@ def test_streamed_private_slices_and_single_pair_many_chunks(ctx, dev, oracle, w
     assert int(streamed(ctx, dev, one, z)[0]) == oracle.count_streamed(one, z)
 
 
+@pytest.mark.parametrize("ndof", [3, 5])
+@pytest.mark.parametrize("n", [260, 772, 1284, 2308, 9220])
+def test_streamed_ring_across_items(ctx, dev, oracle, workloads, n, ndof):
+    """The bulk-tensor ring runs across work items (the first tiles of a warp's next item are requested while the
+    current one is consumed): more items than resident warps, items shorter than / equal to / longer than the ring,
+    every one with a ragged tail, private slices."""
+    n_pairs = 5000 if n < 5000 else 1500
+    pairs = workloads.dataset_pairs(n_pairs, seed=900 + n, shape_variance=(ndof == 5))
+    z = workloads.normal_bank(n_pairs * n, ndof, seed=n + ndof)
+    want = oracle.count_streamed_batch(pairs, z, n, z_pair_stride=n)
+    np.testing.assert_array_equal(streamed(ctx, dev, pairs, z, n=n, z_pair_stride=n), want)
+    np.testing.assert_array_equal(streamed(ctx, dev, pairs, z, n=n, z_pair_stride=n), want)   # (again: zero-invariant scratch)
+
+
 def test_zero_samples_and_accumulate(ctx, dev, oracle, workloads):
     pairs = workloads.dataset_pairs(9, seed=5)
     z = workloads.normal_bank(640, 3, seed=6)

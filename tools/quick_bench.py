@@ -77,7 +77,7 @@ def streamed_part(ctx):
         best, med = time_call(lambda: ctx.count_streamed(d_pairs, pairs.size, z, n, ndof, n, d_hits))
         print(f"streamed shared-bank ndof={ndof} {pairs.size}x{n}: best {best:.3f} ms {pairs.size * n / best / 1e6:.2f} Gtests/s")
     for ndof in (3, 5):
-        npairs, n = 16384, 32768
+        npairs, n = int(os.environ.get("QB_NPAIRS", 16384)), int(os.environ.get("QB_N", 32768))
         torch.manual_seed(ndof)
         z = torch.randn(ndof * npairs * n, device="cuda")          # 6.4 / 10.7 GB
         pp = wl.dataset_pairs(npairs, 9); d_pp = put(pp); d_h = torch.zeros(npairs, dtype=torch.int64, device="cuda")

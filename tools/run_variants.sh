@@ -1,8 +1,9 @@
-run() { # name lib chunk
-  echo "== $1 chunk=$3"
-  if [ "$2" = shipped ]; then SATMC_STREAM_CHUNK=$3 python tools/quick_bench.py --only --streamed 2>&1 | grep -E "private|rror"
-  else SATMC_STREAM_CHUNK=$3 SATMC_LIB=$PWD/variants/$2/libsatmc.so LD_LIBRARY_PATH=$PWD/variants/$2 python tools/quick_bench.py --only --streamed 2>&1 | grep -E "private|rror"; fi
+# development helper: time the streamed kernels of several library builds inside one gpurun call (same box)
+run() { # lib
+  echo "== $1 shape=${QB_NPAIRS:-16384}x${QB_N:-32768}"
+  if [ "$1" = shipped ]; then python tools/quick_bench.py --only --streamed 2>&1 | grep -E "streamed|rror"
+  else SATMC_LIB=$PWD/variants/$1/libsatmc.so LD_LIBRARY_PATH=$PWD/variants/$1 python tools/quick_bench.py --only --streamed 2>&1 | grep -E "streamed|rror"; fi
 }
-for v in shipped s4t128 s2t256 s4t256; do for c in 0 8192 4096 2048; do run $v $v $c; done; done
-run nofinal nofinal 0
-run unpacked unpacked 0
+for v in c3ba shipped; do run $v; done
+export QB_NPAIRS=16001 QB_N=33920
+run shipped
