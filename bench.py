@@ -40,6 +40,10 @@ import time
 
 import numpy as np
 
+# stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner (printed when the environment sets
+# NCCL_DEBUG=VERSION/WARN) goes to stderr instead
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
