@@ -114,24 +114,22 @@ struct CountParams {
     // one is drawn from a device counter that only ever grows; ticket_base is its value when this launch starts
     unsigned long long* ticket; unsigned long long ticket_base;
     // Several work items per counter (n_chunks > 1): contributions are added atomically to `acc`, a scratch array of
-    // the context that holds zeros between launches, and the last block to finish moves the totals to `hits` and
-    // leaves `acc` and `blocks_done` zero again -- one launch, no memset (finalize_counters).  Counter i of the launch
-    // lives at offset (i / fin_inner) * fin_stride + i % fin_inner of both arrays (sweep: one slice of the settings).
+    // the context that holds zeros between launches; the totals are moved to `hits` and `acc` is left zero again by the
+    // kernel itself -- one launch, no memset.  With a known number of contributions per counter (`arrivals` != 0) the
+    // last contribution does it (packed_arrive); otherwise the last block to finish does (finalize_counters_slow,
+    // deferred-queue kernel only).  Counter i of the launch lives at offset (i / fin_inner) * fin_stride +
+    // i % fin_inner of both arrays (sweep: one slice of the settings).
     unsigned long long* acc; unsigned* blocks_done;
     uint64_t n_counters, fin_inner, fin_stride;
     uint64_t hits_len;         // counters behind `hits` (and `acc`): bounds for the -DSATMC_DEBUG build
-    uint32_t arrivals;         // packed scheme (k_count MULTI without DEFER): contributions every counter receives
+    uint32_t arrivals;         // packed scheme: contributions every counter receives (0: irregular, tail pass instead)
 };
 
 // where the atomics of a launch go
-#ifdef SATMC_EXP_NOFINAL
-__device__ __forceinline__ unsigned long long* counter_base(const CountParams& p) { return p.hits; }
-#else
 __device__ __forceinline__ unsigned long long* counter_base(const CountParams& p) { return p.acc ? p.acc : p.hits; }
-#endif
 
-// Packed variant for launches whose every counter receives a known number of contributions (k_count with MULTI and
-// without the deferred queue): arrival count in the top 24 bits of the accumulator, hits in the low 40.  The
+// Packed variant for launches whose every counter receives a known number of contributions (everything but the
+// deferred-queue kernel): arrival count in the top 24 bits of the accumulator, hits in the low 40.  The
 // contribution that completes a counter sees the sum of all earlier ones in the value its own atomic returns, so it
 // moves the total out and clears the accumulator on the spot -- one L2 round trip, no fence, no second counter, no
 // barrier at the end of the kernel (a cfg 2 call is ~15 us in all, of which the fence + arrival + exchange chain of
@@ -203,9 +201,6 @@ __device__ __noinline__ void finalize_counters_slow(const CountParams& p)
 
 __device__ __forceinline__ void finalize_counters(const CountParams& p)
 {
-#ifdef SATMC_EXP_NOFINAL
-    return;
-#endif
     if (p.acc != nullptr && p.arrivals == 0u) finalize_counters_slow(p);   // launch-uniform; packed counters finish themselves
 }
 
