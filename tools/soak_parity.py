@@ -57,6 +57,18 @@ def streamed_case(name, pairs, ndof, n, seed):
     print(f"streamed {name:24s} seed {seed:3d}: {pairs.size * n:.2e} tests (shared bank, ndof {ndof}), mean p {h[0].sum().item() / (pairs.size * n):.4f}, differing pairs {diff}", flush=True)
 
 
+def streamed_private_case(name, pairs, ndof, n, seed):
+    """private HBM-resident slices: the bulk-tensor ring runs across short work items"""
+    global bad
+    d = put(pairs); h = [torch.zeros(pairs.size, dtype=torch.int64, device="cuda") for _ in range(2)]
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    z = torch.randn(ndof * pairs.size * n, device="cuda", generator=g)
+    ctx.count_streamed(d, pairs.size, z, pairs.size * n, ndof, n, h[0], z_pair_stride=n); ctx.synchronize()
+    ctx.count_streamed(d, pairs.size, z, pairs.size * n, ndof, n, h[1], z_pair_stride=n, flags=EXACT); ctx.synchronize()
+    diff = int((h[0] != h[1]).sum().item()); bad += diff
+    print(f"streamed {name:24s} seed {seed:3d}: {pairs.size * n:.2e} tests (private slices, ndof {ndof}), mean p {h[0].sum().item() / (pairs.size * n):.4f}, differing pairs {diff}", flush=True)
+
+
 t0 = time.time()
 rng = np.random.default_rng(2026)
 for s in range(n_seeds):
@@ -84,5 +96,7 @@ for s in range(n_seeds):
     sweep_case("64 settings, 4 theta levels", wl.dataset_pairs(2_000, seed=6000 + s), sig, 20_000, 71 + s)
     streamed_case("dataset prior", wl.dataset_pairs(20_000, seed=7000 + s), 3, 100_000, 81 + s)
     streamed_case("dataset prior, 5-DoF", wl.dataset_pairs(20_000, seed=7500 + s, shape_variance=True), 5, 50_000, 91 + s)
+    streamed_private_case("dataset prior", wl.dataset_pairs(5_000, seed=8000 + s), 3, 40_004 + 4 * s, 101 + s)
+    streamed_private_case("dataset prior, 5-DoF", wl.dataset_pairs(5_000, seed=8500 + s, shape_variance=True), 5, 20_004 + 4 * s, 111 + s)
 print(f"total differing pairs {bad}; {time.time() - t0:.0f} s")
 sys.exit(1 if bad else 0)
