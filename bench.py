@@ -40,9 +40,25 @@ import time
 
 import numpy as np
 
-# stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner (printed when the environment sets
-# NCCL_DEBUG=VERSION/WARN) goes to stderr instead
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line.  NCCL prints its "NCCL version ..." banner to fd 1 from C when the first
+# communicator comes up, and child programs inherit fd 1: the real stdout is set aside for emit() and fd 1 is pointed
+# at stderr for everything else.
+_JSON_FD = None
+
+
+def claim_stdout():
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    fd = 1 if _JSON_FD is None else _JSON_FD
+    while data:
+        data = data[os.write(fd, data):]
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -270,7 +286,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -286,6 +302,7 @@ def main():
     ap.add_argument("--no-programs", action="store_true", help="skip the ztest --gpus N vs --gpus 1 run at N >= 2")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -459,7 +476,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:                # the CPU baselines are N=1 measurements
             line["cpu_baseline"], _, _ = cpu_baseline(pairs, n_samples, seed)
             line["cpu_baselines_c1_c2"] = cpu_baselines_c1_c2(wl)
-        print(json.dumps(line), flush=True)
+        emit(line)
     lib = mod.load_library()
     lib.satmc_host_free(p1); lib.satmc_host_free(p2)
     group.close()
