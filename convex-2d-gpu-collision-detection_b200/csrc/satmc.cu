@@ -145,6 +145,7 @@ int satmc_create(int device, void* stream, satmc_ctx** out)
     if (const char* e = getenv("SATMC_MIN_CHUNK")) { const long v = atol(e); if (v >= 128) ctx->tune_min_chunk = (uint64_t)v / 128 * 128; }
     if (const char* e = getenv("SATMC_STREAM_CHUNK3")) { const long v = atol(e); if (v >= 256) ctx->tune_stream_chunk[0] = (uint64_t)v / 256 * 256; }
     if (const char* e = getenv("SATMC_STREAM_CHUNK5")) { const long v = atol(e); if (v >= 256) ctx->tune_stream_chunk[1] = (uint64_t)v / 256 * 256; }
+    if (const char* e = getenv("SATMC_TINY_BPS")) { const long v = atol(e); if (v >= 0 && v <= 8) ctx->tune_tiny_bps = (int)v; }
     if (const char* e = getenv("SATMC_STREAM_IPW")) { const long v = atol(e); if (v >= 1 && v <= 4096) ctx->tune_stream_ipw = (int)v; }
     if (const char* e = getenv("SATMC_TINY_CHUNK")) { const long v = atol(e); if (v >= 128) ctx->tune_tiny_chunk = (uint64_t)v / 128 * 128; }
     *out = ctx;
@@ -233,13 +234,40 @@ static int plan_items(satmc_ctx* ctx, CountParams& p, int bps, uint64_t& blocks,
     if (p.n_pairs < target_items) {
         n_chunks = (target_items + p.n_pairs - 1) / p.n_pairs;
         const uint64_t max_chunks = (p.n_samples + min_chunk - 1) / min_chunk;
-        if (n_chunks > max_chunks) n_chunks = max_chunks;
+        if (n_chunks > max_chunks) {
+            n_chunks = max_chunks;
+            // the shortest items allowed do not make 8 per warp: at least fill whole rounds of the resident warps
+            // (one pair x 8e6: 3 677 items on 2 368 warps took two rounds, 53 us; 2 315 items take one)
+            const uint64_t rounds = p.n_pairs * n_chunks / resident_warps;
+            if (rounds >= 1 && rounds * resident_warps / p.n_pairs >= 1) n_chunks = rounds * resident_warps / p.n_pairs;
+        }
         if (n_chunks < 1) n_chunks = 1;
         if (p.n_pairs * n_chunks < resident_warps) {              // not even one item per resident warp: cut finer
-            uint64_t want = (resident_warps + p.n_pairs - 1) / p.n_pairs;
+            // A launch this small is over when the busiest SM is: cutting for the resident number of blocks per SM and
+            // then rounding the items to whole sample groups can leave some SMs with 2 blocks and others with 1 (cfg 2:
+            // 245 blocks on 148 SMs).  Candidates: cut for b = bps ... 1 blocks per SM; cost of a candidate = blocks on
+            // the busiest SM x (pair prologue + sample groups per item), with a penalty for running below the resident
+            // occupancy (fewer warps to hide latency behind).  Measured on one pair x 1e6: 20.5 -> 18.1 us by events;
+            // 2e6 and 4e6 samples keep the resident cut (22.2 / 28.9 us against 23.8 / 33.0 when cut for one block).
             const uint64_t max_tiny = (p.n_samples + tiny_chunk - 1) / tiny_chunk;
-            if (want > max_tiny) want = max_tiny;
-            if (want > n_chunks) n_chunks = want;
+            uint64_t best = n_chunks;
+            double best_cost = 0.0;
+            for (int b = bps; b >= 1; b--) {
+                if (ctx->tune_tiny_bps > 0 && b != (ctx->tune_tiny_bps < bps ? ctx->tune_tiny_bps : bps)) continue;
+                const uint64_t fill_warps = (uint64_t)ctx->sm_count * (uint64_t)b * kWarps;
+                uint64_t nc = (fill_warps + p.n_pairs - 1) / p.n_pairs;
+                if (nc > max_tiny) nc = max_tiny;
+                if (nc < n_chunks) nc = n_chunks;
+                if (block_sums && nc >= kWarps) nc = (nc / kWarps) * kWarps;
+                uint64_t ch = (p.n_samples + nc - 1) / nc;
+                ch = ((ch + granule - 1) / granule) * granule;
+                const uint64_t items = p.n_pairs * ((p.n_samples + ch - 1) / ch);
+                const uint64_t blk = (items + kWarps - 1) / kWarps;
+                const uint64_t on_busiest = (blk + (uint64_t)ctx->sm_count - 1) / (uint64_t)ctx->sm_count;
+                const double cost = (double)on_busiest * (1.43 + (double)ch / 128.0) * (on_busiest < (uint64_t)bps ? 1.15 : 1.0);
+                if (best_cost == 0.0 || cost < best_cost) { best_cost = cost; best = nc; }
+            }
+            n_chunks = best;
         }
     }
     if (max_chunk > kMaxChunk) max_chunk = kMaxChunk;

@@ -34,7 +34,7 @@ def main():
         d_h = torch.zeros(1, dtype=torch.int64, device="cuda")
         x = torch.zeros(32, device="cuda")
         print("tiny torch kernel (fill_ of 32 floats): med %.2f us min %.2f us" % med_us(lambda: x.fill_(1.0), s))
-        for n in (128, 4096, 100_000, 1_000_000, 4_000_000, 16_000_000):
+        for n in (128, 4096, 100_000, 200_000, 500_000, 1_000_000, 2_000_000, 4_000_000, 6_000_000, 8_000_000, 12_000_000, 16_000_000, 30_000_000, 60_000_000):
             chunk, n_chunks = ctx.plan_debug(0, 1, n)
             m, lo = med_us(lambda: ctx.count_fused(one, 1, n, 7, d_h), s)
             print(f"1 pair x {n:>9d}: med {m:7.2f} us  min {lo:7.2f} us   chunk {chunk} x {n_chunks} items   {n / m / 1e3:8.2f} Gtests/s")
