@@ -1,2 +1,5 @@
-# development helper: small-call latency, planner's own choice (0) against the resident cut (2)
-for b in 0 2; do echo "== SATMC_TINY_BPS=$b"; SATMC_TINY_BPS=$b python tools/probe_cfg2.py 2>&1 | grep -E "pair x|rror"; done
+# development helper: adaptive batch, current planner against the forced resident cut and an older build
+echo "== shipped"; python tools/probe_adaptive.py 2>&1 | tail -1
+echo "== SATMC_TINY_BPS=2"; SATMC_TINY_BPS=2 python tools/probe_adaptive.py 2>&1 | tail -1
+echo "== build 3ba15c1"; SATMC_LIB=$PWD/variants/c3ba/libsatmc.so LD_LIBRARY_PATH=$PWD/variants/c3ba python tools/probe_adaptive.py 2>&1 | tail -1
+echo "== shipped again"; python tools/probe_adaptive.py 2>&1 | tail -1
