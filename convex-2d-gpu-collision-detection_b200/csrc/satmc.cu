@@ -145,6 +145,7 @@ int satmc_create(int device, void* stream, satmc_ctx** out)
     if (const char* e = getenv("SATMC_MIN_CHUNK")) { const long v = atol(e); if (v >= 128) ctx->tune_min_chunk = (uint64_t)v / 128 * 128; }
     if (const char* e = getenv("SATMC_STREAM_CHUNK3")) { const long v = atol(e); if (v >= 256) ctx->tune_stream_chunk[0] = (uint64_t)v / 256 * 256; }
     if (const char* e = getenv("SATMC_STREAM_CHUNK5")) { const long v = atol(e); if (v >= 256) ctx->tune_stream_chunk[1] = (uint64_t)v / 256 * 256; }
+    if (const char* e = getenv("SATMC_FUSED_MAX_CHUNK")) { const long long v = atoll(e); if (v >= 32768 && v <= (1ll << 31)) ctx->tune_fused_max_chunk = (uint64_t)v / 128 * 128; }
     if (const char* e = getenv("SATMC_TINY_BPS")) { const long v = atol(e); if (v >= 0 && v <= 8) ctx->tune_tiny_bps = (int)v; }
     if (const char* e = getenv("SATMC_STREAM_IPW")) { const long v = atol(e); if (v >= 1 && v <= 4096) ctx->tune_stream_ipw = (int)v; }
     if (const char* e = getenv("SATMC_TINY_CHUNK")) { const long v = atol(e); if (v >= 128) ctx->tune_tiny_chunk = (uint64_t)v / 128 * 128; }
@@ -297,7 +298,7 @@ extern "C" int satmc_plan_debug(satmc_ctx* ctx, int kind, uint64_t n_pairs, uint
     CountParams p{}; p.n_pairs = n_pairs; p.n_samples = n_samples;
     uint64_t blocks = 0;
     int rc;
-    if (kind == 0) rc = plan_items(ctx, p, ctx->blocks_per_sm, blocks, 8, 1ull << 20);
+    if (kind == 0) rc = plan_items(ctx, p, ctx->blocks_per_sm, blocks, 8, ctx->tune_fused_max_chunk);
     else if (kind == 1) rc = plan_items(ctx, p, ctx->blocks_per_sm_streamed, blocks);
     else if (kind == 2) rc = plan_items(ctx, p, 2, blocks);
     else rc = plan_items(ctx, p, SATMC_SWEEP_BPS, blocks, 32, kMaxChunk, kSweepWarps);
@@ -379,14 +380,16 @@ static int launch_count(satmc_ctx* ctx, const Src& src, CountParams p, bool time
     const int bps = tma ? ctx->blocks_per_sm_tma[p.ndof == 5][shared_bank] : (STREAMED ? ctx->blocks_per_sm_streamed : ctx->blocks_per_sm);
     uint64_t blocks = 0;
     // Long items (few pairs, many samples each -- cfg 4, cfg 5): undecided sample groups are queued per warp and worked
-    // off 32 at a time (ColdQueue, k_count<.., DEFER = true>).  Items are capped at 2^20 samples so that the queue holds an
-    // item's undecided groups at the rates seen in practice (<= 2.4e-4 per test).  Short items keep the immediate path:
-    // there the queue's bookkeeping costs more than the few undecided groups of an item.
+    // off 32 at a time (ColdQueue, k_count<.., DEFER = true>).  Items are capped at 2^18 samples: the queue then holds an
+    // item's undecided groups at the rates seen in practice (<= 2.4e-4 per test), and a warp gets enough items for the
+    // dynamic distribution to even out the speed differences between SMs (a cfg 4 share of 1.25e10 samples: 8 items of
+    // 5 ms per warp at a cap of 2^20 took 39.8 ms, 24 items per warp take 38.4).  Short items (< 32768 samples) keep the
+    // immediate path: there the queue's bookkeeping costs more than the few undecided groups of an item.
     // Bulk-tensor kernel on private banks (HBM bound): short items keep the addresses the resident warps stream from
     // close together; the ring runs across items, so a switch costs only the pair prologue.  Measured on five bank
     // shapes (profiles/r2_streamed_ring_experiments.log): 3-DoF 6.0-6.3 -> 6.6-6.8 TB/s with items of 2048 samples,
     // 5-DoF 6.6-6.9 -> 6.8-6.95 TB/s with 8192.  A shared (L2-resident) bank is issue bound: items stay long.
-    uint64_t max_chunk = STREAMED ? (1ull << 36) : (1ull << 20);
+    uint64_t max_chunk = STREAMED ? (1ull << 36) : ctx->tune_fused_max_chunk;
     if (tma && !shared_bank) max_chunk = ctx->tune_stream_chunk[p.ndof == 5];
     int rc = plan_items(ctx, p, bps, blocks, tma ? ctx->tune_stream_ipw : 8, max_chunk, kWarps, tma ? (uint64_t)tile : 128, !tma);
     if (rc) return rc;
@@ -466,7 +469,7 @@ bool satmc_fused_is_multi(satmc_ctx* ctx, uint64_t n_pairs, uint64_t n_samples)
 {
     CountParams p{}; p.n_pairs = n_pairs; p.n_samples = n_samples;
     uint64_t blocks = 0;
-    if (n_pairs == 0 || n_samples == 0 || plan_items(ctx, p, ctx->blocks_per_sm, blocks, 8, 1ull << 20)) return false;
+    if (n_pairs == 0 || n_samples == 0 || plan_items(ctx, p, ctx->blocks_per_sm, blocks, 8, ctx->tune_fused_max_chunk)) return false;
     return p.n_chunks > 1;
 }
 

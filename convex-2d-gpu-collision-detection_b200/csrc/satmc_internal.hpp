@@ -41,6 +41,7 @@ struct satmc_ctx {
     int* h_word = nullptr;                   // pinned: the adaptive loop's "pairs left" comes back here
     uint64_t tune_min_chunk = 2048, tune_tiny_chunk = 256;   // planner: samples per work item (see plan_items)
     uint64_t tune_stream_chunk[2] = {2048, 8192};            // planner: most samples per work item, bulk-tensor path on private banks (3-DoF, 5-DoF)
+    uint64_t tune_fused_max_chunk = 1ull << 18;              // planner: most samples per work item of the fused kernels (see launch_count)
     int tune_tiny_bps = 0;                                   // planner: blocks per SM a tiny launch is cut for (0: the resident number)
     int tune_stream_ipw = 8;                                 // planner: work items per resident warp, streamed bulk-tensor path
 };

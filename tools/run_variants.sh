@@ -1,5 +1,2 @@
-# development helper: adaptive batch, current planner against the forced resident cut and an older build
-echo "== shipped"; python tools/probe_adaptive.py 2>&1 | tail -1
-echo "== SATMC_TINY_BPS=2"; SATMC_TINY_BPS=2 python tools/probe_adaptive.py 2>&1 | tail -1
-echo "== build 3ba15c1"; SATMC_LIB=$PWD/variants/c3ba/libsatmc.so LD_LIBRARY_PATH=$PWD/variants/c3ba python tools/probe_adaptive.py 2>&1 | tail -1
-echo "== shipped again"; python tools/probe_adaptive.py 2>&1 | tail -1
+# development helper: long single-pair calls against the fused item cap
+for c in 1048576 262144 131072 65536 32768; do echo "== SATMC_FUSED_MAX_CHUNK=$c"; SATMC_FUSED_MAX_CHUNK=$c python tools/probe_long.py 12.5e9 25e9 2e9 2>&1 | grep -E "pair x|rror"; done
