@@ -208,6 +208,23 @@ def test_item_sample_cap(ctx, dev, workloads):
     assert int(fused(ctx, dev, one, n, 3)[0]) == n
 
 
+def test_planner_balances_small_and_long_single_pair_calls(ctx):
+    """Planner properties the measured latencies rest on: a cfg 2 call (one pair x 1e6) is cut so
+    that no SM gets two blocks while others get one; a clamped chunking fills whole rounds of the resident warps; a long
+    single-pair call (a cfg 4 share) gets many items per warp, none above the fused cap of 2^18 samples."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    resident_warps = sms * 2 * 8
+    chunk, n_chunks = ctx.plan_debug(0, 1, 1_000_000)
+    blocks = -(-n_chunks // 8)
+    assert chunk % 128 == 0 and chunk * n_chunks >= 1_000_000
+    assert blocks <= sms or blocks % sms == 0, (chunk, n_chunks, blocks, sms)
+    chunk, n_chunks = ctx.plan_debug(0, 1, 8_000_000)
+    assert n_chunks <= resident_warps, (chunk, n_chunks)             # one round, not one and a half
+    chunk, n_chunks = ctx.plan_debug(0, 1, 12_500_000_000)
+    assert chunk <= 1 << 18 and n_chunks >= 16 * resident_warps, (chunk, n_chunks)
+
+
 def test_c_client_of_the_group_api(satmc, tmp_path):
     """tests/c/group_example.c (plain C99): satmc_group_create over every GPU of the box, both shard modes through host
     buffers, the counts equal satmc_count_fused_host on one device."""
