@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, STREAMED ? SATMC_MIN_BLOCKS_STREAMED
 #define SATMC_STREAMED_PACKED 1
 #endif
 // Ring geometry per sample layout and bank kind (measured on B200, profiles/r2_streamed_ring_experiments.log), all at
-// 2 blocks per SM.  The 3-DoF loop is short (45 instructions per test), so the per-tile bookkeeping and the bytes in
+// 2 blocks per SM.  The 3-DoF loop is short (40 instructions per test), so the per-tile bookkeeping and the bytes in
 // flight per warp decide: 4 stages of 256 samples (no spills at 128 registers).  The 5-DoF loop streams private banks
 // from HBM best with 2 stages of 128 samples (6.9 vs 6.4 TB/s with 256), while on a shared, L2-resident bank it is
 // issue bound and 256-sample tiles halve the per-tile bookkeeping (526 vs 465 Gtests/s).
